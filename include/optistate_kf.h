@@ -1,0 +1,175 @@
+/*
+ * optistate_kf.h - C ABI of the B200-native batched Kalman filter for OptiState's estimation hot path.
+ *
+ * One shared library (liboptistate_kf.so, built for sm_100a) exports exactly these entry points.  They are
+ * what a foreign-function binding of the reference would bind in place of its NumPy filter:
+ *
+ *   optistate_kf_batch      replaces the per-step call chain of the reference driver,
+ *                           get_odom -> set_measurements -> predict(p, f) -> update()
+ *                           (/root/reference/kalman_filter/kalman_filter.py:79-138,164-174 and
+ *                            /root/reference/misc/force_controller.py:269-291), looped over T steps as in
+ *                           /root/reference/data_collection/data_conversion_Kalman_to_Training.py:193-201,
+ *                           for N independent trajectories at once.  With `phases` it also serves the
+ *                           single calls Kalman_Filter.predict / .update / .predict_mpc (covariance part,
+ *                           kalman_filter.py:153-161) make.
+ *   optistate_kf_measure    replaces get_odom + set_measurements (kalman_filter.py:79-117) for S streams x T steps.
+ *   optistate_fma_peak      measures the FP64 / FP32 FMA issue peak of the device (roofline denominator).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every pointer is a NON-OWNING DEVICE pointer unless stated otherwise;
+ *     the library never allocates device memory and keeps no state besides a launch counter (re-entrant,
+ *     thread-safe).
+ *   - calls are asynchronous on the CUDA stream passed as `void* cuda_stream` (a cudaStream_t; NULL = default).
+ *   - return value: 0 on success, a negative OPTI_KF_E_* code otherwise; nothing is thrown across the boundary.
+ *     Per-trajectory numerical events (the reference's exceptions) are reported in `status[N]` bit masks.
+ *   - layouts are structure-of-arrays with the trajectory / stream index fastest-varying:
+ *       per-step inputs    [T][C][S]   element (t, c, s) at ((t*C + c)*S + s)
+ *       per-step outputs   [T][C][N]
+ *       per-trajectory     [C][N]
+ *     Trajectory i reads base stream  stream_index[i]  or, when stream_index is NULL, (i + stream_offset) % S.
+ *   - all floating-point arrays of one call share the scalar type `dtype` (double or float).
+ */
+#ifndef OPTISTATE_KF_H_
+#define OPTISTATE_KF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPTISTATE_KF_ABI_VERSION 1
+
+#define OPTI_KF_NX 12 /* states  [thx thy thz | x y z | wx wy wz | vx vy vz]   kalman_filter.py:9  */
+#define OPTI_KF_NZ 10 /* measurements [th_imu(3) z_odom w_imu(3) v_odom(3)]    kalman_filter.py:11 */
+#define OPTI_KF_SUMMARY_ROWS 52
+
+/* dtype */
+enum { OPTI_KF_F64 = 0, OPTI_KF_F32 = 1 };
+
+/* algo
+ *   JOINT       the reference's operand order on a full (not symmetrised) 12x12 P:  S = H P H^T + R,
+ *               K = (P H^T) S^-1 by a Cholesky solve, P <- P - K (H P); dense Q / R / P0 allowed; emits K.
+ *   SEQUENTIAL  diagonal R and Q, symmetric P0: the 10 measurements are folded in one at a time on a packed
+ *               symmetric P held in registers (algebraically identical for diagonal R; parity to <=1e-12 of the
+ *               reference is part of the test-suite).  This is the throughput path.
+ *   AUTO        SEQUENTIAL when the descriptor allows it, JOINT otherwise.                                   */
+enum { OPTI_KF_ALGO_AUTO = 0, OPTI_KF_ALGO_JOINT = 1, OPTI_KF_ALGO_SEQUENTIAL = 2 };
+
+/* cov_model: 0 = predict():      F_d = I + dt F               (kalman_filter.py:125-135)
+ *            1 = predict_mpc():  F_d = exp(dt F) element-wise, R from body_ref angles (kalman_filter.py:153-158);
+ *                JOINT only, needs `body_ref`.                                                                */
+enum { OPTI_KF_COV_PREDICT = 0, OPTI_KF_COV_MPC = 1 };
+
+/* phases: which parts of a step run (all three for the batched recursion) */
+enum { OPTI_KF_PHASE_MEASURE = 1, OPTI_KF_PHASE_PREDICT = 2, OPTI_KF_PHASE_UPDATE = 4, OPTI_KF_PHASE_ALL = 7 };
+
+/* noise / initial-covariance array kinds */
+enum {
+    OPTI_KF_MAT_NONE = 0,       /* pointer ignored (P0: use Q, as settings.py:31 does)        */
+    OPTI_KF_MAT_DIAG = 1,       /* [n]        one diagonal shared by every trajectory          */
+    OPTI_KF_MAT_DIAG_PER = 2,   /* [n][N]     one diagonal per trajectory                      */
+    OPTI_KF_MAT_DENSE = 3,      /* [n*n]      one dense row-major matrix shared                */
+    OPTI_KF_MAT_DENSE_PER = 4   /* [n*n][N]   one dense row-major matrix per trajectory        */
+};
+
+/* status[i] bits */
+enum {
+    OPTI_KF_ST_NOT_PD = 1,     /* a pivot of S was <= 0 or not finite (reference: LinAlgError / garbage)      */
+    OPTI_KF_ST_NONFINITE = 2,  /* a state became inf/nan                                                        */
+    OPTI_KF_ST_ALL_SWING = 4,  /* a step had sum(contact) == 0 (reference raises ValueError, kalman_filter.py:97-103);
+                                  the odometry part of z is set to 0 for that step                              */
+    OPTI_KF_ST_ASYMMETRIC = 8  /* JOINT: S was visibly asymmetric; the Cholesky solve used its lower triangle   */
+};
+
+/* error codes */
+enum {
+    OPTI_KF_OK = 0,
+    OPTI_KF_E_NULL = -1,        /* descriptor or a required pointer is NULL                 */
+    OPTI_KF_E_VERSION = -2,     /* struct_size / abi_version mismatch                        */
+    OPTI_KF_E_DTYPE = -3,
+    OPTI_KF_E_SHAPE = -4,       /* negative / zero sizes, bad ckpt_every, bad kinds          */
+    OPTI_KF_E_UNSUPPORTED = -5, /* combination not available for the requested algo          */
+    OPTI_KF_E_CUDA = -6,        /* the CUDA runtime reported an error at launch              */
+    OPTI_KF_E_NO_DEVICE = -7
+};
+
+typedef struct OptiKfDesc {
+    uint32_t struct_size; /* sizeof(OptiKfDesc) */
+    uint32_t abi_version; /* OPTISTATE_KF_ABI_VERSION */
+    int32_t dtype, algo, cov_model, phases;
+    int64_t n_traj, n_steps, n_streams, stream_offset;
+    double dt, mass, inertia[3], gravity; /* settings.py:5,11,20-23; kalman_filter.py:56 */
+
+    /* per-step inputs [T][C][S]; which are required depends on `phases` */
+    const void *imu;      /* C=6   MEASURE                                   */
+    const void *p;        /* C=12  MEASURE, PREDICT (body-frame feet)        */
+    const void *dp;       /* C=12  MEASURE                                   */
+    const void *contact;  /* C=4   MEASURE (0/1 flags stored as dtype)       */
+    const void *f;        /* C=12  PREDICT (world-frame forces)              */
+    const void *z_in;     /* C=10  UPDATE without MEASURE (pre-formed z)     */
+    const void *body_ref; /* C=12  cov_model == OPTI_KF_COV_MPC              */
+    const void *truth;    /* C=12  optional label stream for the summary     */
+    const void *nominal;  /* C=12  optional second label stream (summary)    */
+    const int32_t *stream_index; /* [N] or NULL */
+
+    /* initial state and noise */
+    const void *x0; int32_t x0_per_traj;  /* [12] or [12][N] */
+    int32_t p0_kind, q_kind, r_kind;
+    const void *P0, *Q, *R;
+
+    /* outputs, every one optional (NULL = not wanted) */
+    void *x_steps;        /* [T][12][N] posterior state after update      */
+    void *x_model_steps;  /* [T][12][N] predicted state (KF.x_model)      */
+    void *p_world_steps;  /* [T][12][N] feet rotated into the world frame (the in-place mutation of
+                             force_controller.py:274-277)                 */
+    void *z_steps;        /* [T][10][N]                                   */
+    void *p_trace_steps;  /* [T][N]  trace(P) after update                */
+    void *k_gain_steps;   /* [T][N]  sum_{i<10} K[i][i]  (np.trace of the 12x10 gain) */
+    void *nis_steps;      /* [T][N]  y^T S^-1 y                            */
+    int64_t ckpt_every;   /* P checkpoints after steps ckpt_every, 2*ckpt_every, ... (0 = none) */
+    void *P_ckpt;         /* [T/ckpt_every][144][N] row-major P           */
+    void *x_final;        /* [12][N]                                      */
+    void *P_final;        /* [144][N]                                     */
+    void *K_final;        /* [120][N] row-major 12x10 gain of the last step (JOINT only) */
+    void *summary;        /* [OPTI_KF_SUMMARY_ROWS][N]: 0-11 final x, 12-23 diag P, 24-35 RMSE vs truth,
+                             36-47 RMS deviation from nominal, 48 mean NIS, 49 trace P, 50 K gain,
+                             51 sqrt(max_t NIS_t)                          */
+    uint32_t *status;     /* [N] */
+} OptiKfDesc;
+
+typedef struct OptiKfMeasureDesc {
+    uint32_t struct_size, abi_version;
+    int32_t dtype, reserved;
+    int64_t n_steps, n_streams;
+    const void *imu, *p, *dp, *contact; /* [T][6|12|12|4][S] */
+    void *z;                            /* [T][10][S] */
+    void *odom;                         /* [T][4][S] optional: z_odom, vx, vy, vz (get_odom's return value) */
+    uint32_t *status;                   /* [S] optional, OPTI_KF_ST_ALL_SWING */
+} OptiKfMeasureDesc;
+
+/* Runs the filter; dtype taken from the descriptor. */
+int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);
+/* Same, asserting the scalar type (the two names a binding would import). */
+int optistate_kf_batch_f64(const OptiKfDesc *desc, void *cuda_stream);
+int optistate_kf_batch_f32(const OptiKfDesc *desc, void *cuda_stream);
+/* Batched measurement formation. */
+int optistate_kf_measure(const OptiKfMeasureDesc *desc, void *cuda_stream);
+/* Which algo optistate_kf_batch would run for this descriptor (OPTI_KF_ALGO_JOINT / _SEQUENTIAL) or an error. */
+int optistate_kf_resolve_algo(const OptiKfDesc *desc);
+/* Scratch memory the call needs: always 0 today (everything lives in registers / shared memory). */
+int optistate_kf_workspace_bytes(const OptiKfDesc *desc, size_t *bytes_out);
+/* FMA-chain micro-benchmark: sustained FLOP/s (2 per FMA) of dependent-free FMA issue on the current device.
+ * Synchronises the stream (it has to time the kernel).  seconds_out may be NULL. */
+int optistate_fma_peak(int dtype, int64_t fma_per_thread, double *flops_per_s_out, double *seconds_out, void *cuda_stream);
+/* Number of kernel launches this library has made in this process (for bench.py's gpu_launches claim). */
+int64_t optistate_kf_launch_count(void);
+const char *optistate_kf_strerror(int code);
+int optistate_kf_abi_version(void);
+size_t optistate_kf_desc_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTISTATE_KF_H_ */

@@ -1,0 +1,259 @@
+// extern "C" boundary of liboptistate_kf.so (see include/optistate_kf.h): descriptor validation, conversion of
+// the POD descriptor into typed kernel parameters, kernel selection and launch.  No torch types, no allocation,
+// no exceptions; every failure is a negative return code.
+#include <atomic>
+#include <cstring>
+
+#include "kf_joint.cuh"
+#include "kf_seq.cuh"
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+bool is_diag_kind(int k) { return k == OPTI_KF_MAT_DIAG || k == OPTI_KF_MAT_DIAG_PER; }
+bool valid_kind(int k, bool allow_none) { return (k >= (allow_none ? 0 : 1)) && k <= OPTI_KF_MAT_DENSE_PER; }
+
+int validate(const OptiKfDesc *d) {
+    if (!d) return OPTI_KF_E_NULL;
+    if (d->struct_size != sizeof(OptiKfDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
+    if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (d->n_traj < 0 || d->n_steps < 0 || d->n_streams <= 0 || d->ckpt_every < 0) return OPTI_KF_E_SHAPE;
+    if (d->phases <= 0 || d->phases > OPTI_KF_PHASE_ALL) return OPTI_KF_E_SHAPE;
+    if (d->algo < OPTI_KF_ALGO_AUTO || d->algo > OPTI_KF_ALGO_SEQUENTIAL) return OPTI_KF_E_SHAPE;
+    if (d->cov_model != OPTI_KF_COV_PREDICT && d->cov_model != OPTI_KF_COV_MPC) return OPTI_KF_E_SHAPE;
+    if (!valid_kind(d->q_kind, false) || !valid_kind(d->r_kind, false) || !valid_kind(d->p0_kind, true)) return OPTI_KF_E_SHAPE;
+    if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0)) return OPTI_KF_E_SHAPE;
+    if (!d->x0 || !d->Q || !d->R) return OPTI_KF_E_NULL;
+    if (d->p0_kind != OPTI_KF_MAT_NONE && !d->P0) return OPTI_KF_E_NULL;
+    if ((d->phases & OPTI_KF_PHASE_MEASURE) && (!d->imu || !d->p || !d->dp || !d->contact)) return OPTI_KF_E_NULL;
+    if ((d->phases & OPTI_KF_PHASE_PREDICT) && (!d->p || !d->f)) return OPTI_KF_E_NULL;
+    if ((d->phases & OPTI_KF_PHASE_UPDATE) && !(d->phases & OPTI_KF_PHASE_MEASURE) && !d->z_in) return OPTI_KF_E_NULL;
+    if (d->cov_model == OPTI_KF_COV_MPC && (d->phases & OPTI_KF_PHASE_PREDICT) && !d->body_ref) return OPTI_KF_E_NULL;
+    if (d->P_ckpt && d->ckpt_every == 0) return OPTI_KF_E_SHAPE;
+    if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
+    return OPTI_KF_OK;
+}
+
+// SEQUENTIAL covers the full recursion with diagonal noise; everything else is JOINT.
+bool sequential_ok(const OptiKfDesc *d) {
+    return is_diag_kind(d->q_kind) && is_diag_kind(d->r_kind) && d->cov_model == OPTI_KF_COV_PREDICT &&
+           d->K_final == nullptr &&
+           (d->phases == OPTI_KF_PHASE_ALL || (d->phases == (OPTI_KF_PHASE_PREDICT | OPTI_KF_PHASE_UPDATE) && d->z_in));
+}
+
+int resolve(const OptiKfDesc *d) {
+    if (d->algo == OPTI_KF_ALGO_JOINT) return OPTI_KF_ALGO_JOINT;
+    if (d->algo == OPTI_KF_ALGO_SEQUENTIAL) return sequential_ok(d) ? OPTI_KF_ALGO_SEQUENTIAL : OPTI_KF_E_UNSUPPORTED;
+    // AUTO: a dense P0 may be non-symmetric, which only JOINT reproduces; the host asks for SEQUENTIAL explicitly
+    // once it has checked symmetry.
+    const bool p0_sym = d->p0_kind == OPTI_KF_MAT_NONE || is_diag_kind(d->p0_kind);
+    return (sequential_ok(d) && p0_sym) ? OPTI_KF_ALGO_SEQUENTIAL : OPTI_KF_ALGO_JOINT;
+}
+
+template <typename Real>
+okf::Params<Real> make_params(const OptiKfDesc *d) {
+    okf::Params<Real> p;
+    std::memset(&p, 0, sizeof p);
+    p.N = d->n_traj; p.T = d->n_steps; p.S = d->n_streams; p.stream_offset = d->stream_offset;
+    p.phases = d->phases; p.cov_model = d->cov_model;
+    p.dt = (Real)d->dt;
+    p.dt_over_m = (Real)((1.0 / d->mass) * d->dt);  // B*dt with B = 1/m (force_controller.py:246-247,289)
+    p.dt_g = (Real)(d->dt * d->gravity);
+    for (int k = 0; k < 3; ++k) p.inv_inertia[k] = (Real)(1.0 / d->inertia[k]);
+    p.imu = (const Real *)d->imu; p.p = (const Real *)d->p; p.dp = (const Real *)d->dp;
+    p.contact = (const Real *)d->contact; p.f = (const Real *)d->f;
+    p.z_in = (d->phases & OPTI_KF_PHASE_MEASURE) ? nullptr : (const Real *)d->z_in;
+    p.body_ref = (const Real *)d->body_ref; p.truth = (const Real *)d->truth; p.nominal = (const Real *)d->nominal;
+    p.stream_index = d->stream_index;
+    p.x0 = (const Real *)d->x0; p.x0_ld = d->x0_per_traj ? d->n_traj : 1; p.x0_inc = d->x0_per_traj ? 1 : 0;
+    p.P0 = (const Real *)d->P0; p.p0_kind = d->p0_kind;
+    p.Q = (const Real *)d->Q; p.q_kind = d->q_kind;
+    p.R = (const Real *)d->R; p.r_kind = d->r_kind;
+    p.x_steps = (Real *)d->x_steps; p.x_model_steps = (Real *)d->x_model_steps; p.p_world_steps = (Real *)d->p_world_steps;
+    p.z_steps = (Real *)d->z_steps; p.p_trace_steps = (Real *)d->p_trace_steps; p.k_gain_steps = (Real *)d->k_gain_steps;
+    p.nis_steps = (Real *)d->nis_steps; p.ckpt_every = d->ckpt_every; p.P_ckpt = (Real *)d->P_ckpt;
+    p.x_final = (Real *)d->x_final; p.P_final = (Real *)d->P_final; p.K_final = (Real *)d->K_final;
+    p.summary = (Real *)d->summary; p.status = d->status;
+    return p;
+}
+
+template <typename Real>
+int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
+    if (d->n_traj == 0) return OPTI_KF_OK;
+    const okf::Params<Real> p = make_params<Real>(d);
+    cudaGetLastError();
+    if (algo == OPTI_KF_ALGO_SEQUENTIAL) {
+        constexpr int kThreads = 128;
+        const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);
+        const size_t smem = (size_t)okf::SEQ_NOISE_ROWS * kThreads * sizeof(Real);
+        if (d->summary)
+            okf::kf_seq_kernel<Real, true><<<blocks, kThreads, smem, stream>>>(p);
+        else
+            okf::kf_seq_kernel<Real, false><<<blocks, kThreads, smem, stream>>>(p);
+    } else {
+        constexpr int kThreads = 64;
+        const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);
+        okf::kf_joint_kernel<Real><<<blocks, kThreads, 0, stream>>>(p);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
+// ---- batched get_odom + set_measurements ---------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) kf_measure_kernel(long long T, long long S, const Real *__restrict__ imu,
+                                                         const Real *__restrict__ p, const Real *__restrict__ dp,
+                                                         const Real *__restrict__ contact, Real *__restrict__ z,
+                                                         Real *__restrict__ odom, uint32_t *__restrict__ status) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (t, s) flattened, s fastest
+    if (idx >= T * S) return;
+    const long long t = idx / S, s = idx % S;
+    Real im[6], pp[12], dd[12], cc[4], zz[okf::NZ];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) im[c] = imu[(t * 6 + c) * S + s];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) { pp[c] = p[(t * 12 + c) * S + s]; dd[c] = dp[(t * 12 + c) * S + s]; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cc[c] = contact[(t * 4 + c) * S + s];
+    const bool all_swing = okf::form_measurement(im, pp, dd, cc, zz);
+    if (z) {
+#pragma unroll
+        for (int c = 0; c < okf::NZ; ++c) z[(t * okf::NZ + c) * S + s] = zz[c];
+    }
+    if (odom) {
+        odom[(t * 4 + 0) * S + s] = zz[3];
+        odom[(t * 4 + 1) * S + s] = zz[7];
+        odom[(t * 4 + 2) * S + s] = zz[8];
+        odom[(t * 4 + 3) * S + s] = zz[9];
+    }
+    if (status && all_swing) atomicOr(status + s, (uint32_t)OPTI_KF_ST_ALL_SWING);
+}
+
+// ---- FMA issue-peak micro-benchmark ----------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) fma_peak_kernel(long long iters, Real seed, Real *sink) {
+    Real a[16];
+    const Real m = Real(0.999) + seed * Real(1e-9), c = Real(1e-3) * (Real)(threadIdx.x & 7);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + (Real)k;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = a[k] * m + c;
+    }
+    Real s = Real(0);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == Real(-12345.678)) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true; keeps the chain alive
+}
+
+template <typename Real>
+int fma_peak(long long fma_per_thread, double *flops_out, double *seconds_out, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return OPTI_KF_E_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    const long long iters = (fma_per_thread + 15) / 16;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return OPTI_KF_E_CUDA;
+    fma_peak_kernel<Real><<<blocks, threads, 0, stream>>>(iters / 8 + 1, Real(1), nullptr);  // warm-up
+    cudaEventRecord(e0, stream);
+    fma_peak_kernel<Real><<<blocks, threads, 0, stream>>>(iters, Real(1), nullptr);
+    cudaEventRecord(e1, stream);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return OPTI_KF_E_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double fma = (double)iters * 16.0 * (double)blocks * (double)threads;
+    if (flops_out) *flops_out = 2.0 * fma / ((double)ms * 1e-3);
+    if (seconds_out) *seconds_out = (double)ms * 1e-3;
+    return OPTI_KF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int optistate_kf_abi_version(void) { return OPTISTATE_KF_ABI_VERSION; }
+size_t optistate_kf_desc_size(void) { return sizeof(OptiKfDesc); }
+int64_t optistate_kf_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+int optistate_kf_resolve_algo(const OptiKfDesc *desc) {
+    const int rc = validate(desc);
+    return rc != OPTI_KF_OK ? rc : resolve(desc);
+}
+
+int optistate_kf_workspace_bytes(const OptiKfDesc *desc, size_t *bytes_out) {
+    const int rc = validate(desc);
+    if (rc != OPTI_KF_OK) return rc;
+    if (!bytes_out) return OPTI_KF_E_NULL;
+    *bytes_out = 0;
+    return OPTI_KF_OK;
+}
+
+int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream) {
+    const int rc = validate(desc);
+    if (rc != OPTI_KF_OK) return rc;
+    const int algo = resolve(desc);
+    if (algo < 0) return algo;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    return desc->dtype == OPTI_KF_F64 ? launch<double>(desc, algo, stream) : launch<float>(desc, algo, stream);
+}
+
+int optistate_kf_batch_f64(const OptiKfDesc *desc, void *cuda_stream) {
+    if (desc && desc->dtype != OPTI_KF_F64) return OPTI_KF_E_DTYPE;
+    return optistate_kf_batch(desc, cuda_stream);
+}
+
+int optistate_kf_batch_f32(const OptiKfDesc *desc, void *cuda_stream) {
+    if (desc && desc->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    return optistate_kf_batch(desc, cuda_stream);
+}
+
+int optistate_kf_measure(const OptiKfMeasureDesc *d, void *cuda_stream) {
+    if (!d) return OPTI_KF_E_NULL;
+    if (d->struct_size != sizeof(OptiKfMeasureDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
+    if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (d->n_steps < 0 || d->n_streams <= 0) return OPTI_KF_E_SHAPE;
+    if (!d->imu || !d->p || !d->dp || !d->contact || (!d->z && !d->odom)) return OPTI_KF_E_NULL;
+    const long long total = d->n_steps * d->n_streams;
+    if (total == 0) return OPTI_KF_OK;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    cudaGetLastError();
+    if (d->dtype == OPTI_KF_F64)
+        kf_measure_kernel<double><<<blocks, 256, 0, stream>>>(d->n_steps, d->n_streams, (const double *)d->imu, (const double *)d->p,
+                                                              (const double *)d->dp, (const double *)d->contact, (double *)d->z,
+                                                              (double *)d->odom, d->status);
+    else
+        kf_measure_kernel<float><<<blocks, 256, 0, stream>>>(d->n_steps, d->n_streams, (const float *)d->imu, (const float *)d->p,
+                                                             (const float *)d->dp, (const float *)d->contact, (float *)d->z,
+                                                             (float *)d->odom, d->status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
+int optistate_fma_peak(int dtype, int64_t fma_per_thread, double *flops_per_s_out, double *seconds_out, void *cuda_stream) {
+    if (fma_per_thread <= 0) return OPTI_KF_E_SHAPE;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (dtype == OPTI_KF_F64) return fma_peak<double>(fma_per_thread, flops_per_s_out, seconds_out, stream);
+    if (dtype == OPTI_KF_F32) return fma_peak<float>(fma_per_thread, flops_per_s_out, seconds_out, stream);
+    return OPTI_KF_E_DTYPE;
+}
+
+const char *optistate_kf_strerror(int code) {
+    switch (code) {
+        case OPTI_KF_OK: return "ok";
+        case OPTI_KF_E_NULL: return "descriptor or a required pointer is NULL";
+        case OPTI_KF_E_VERSION: return "descriptor size / ABI version mismatch";
+        case OPTI_KF_E_DTYPE: return "unsupported or mismatching dtype";
+        case OPTI_KF_E_SHAPE: return "invalid sizes, kinds or constants";
+        case OPTI_KF_E_UNSUPPORTED: return "combination not supported by the requested algo";
+        case OPTI_KF_E_CUDA: return "CUDA runtime error at launch";
+        case OPTI_KF_E_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+}  // extern "C"

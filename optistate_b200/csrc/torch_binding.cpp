@@ -1,0 +1,201 @@
+// Thin PyTorch C++ extension over the C ABI of liboptistate_kf.so: unwraps tensors into raw device pointers,
+// checks device / dtype / contiguity / element counts (the C ABI cannot), takes torch's current CUDA stream and
+// calls the extern "C" entry points.  No arithmetic happens here and there is no CPU path: CPU tensors are an error.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <map>
+#include <optional>
+#include <string>
+
+#include "../../include/optistate_kf.h"
+
+namespace {
+
+using TensorMap = std::map<std::string, at::Tensor>;
+
+struct Checker {
+    at::ScalarType st;
+    c10::Device dev;
+    const void *get(const TensorMap &m, const char *name, int64_t numel, bool required) const {
+        auto it = m.find(name);
+        if (it == m.end()) {
+            TORCH_CHECK(!required, "optistate_b200: missing tensor '", name, "'");
+            return nullptr;
+        }
+        const at::Tensor &t = it->second;
+        TORCH_CHECK(t.is_cuda(), "optistate_b200: '", name, "' must be a CUDA tensor (there is no CPU path)");
+        TORCH_CHECK(t.device() == dev, "optistate_b200: '", name, "' is on ", t.device(), ", expected ", dev);
+        TORCH_CHECK(t.scalar_type() == st, "optistate_b200: '", name, "' has dtype ", t.scalar_type(), ", expected ", st);
+        TORCH_CHECK(t.is_contiguous(), "optistate_b200: '", name, "' must be contiguous");
+        TORCH_CHECK(t.numel() == numel, "optistate_b200: '", name, "' has ", t.numel(), " elements, expected ", numel);
+        return t.data_ptr();
+    }
+};
+
+int64_t geti(const std::map<std::string, int64_t> &c, const char *k, int64_t dflt) {
+    auto it = c.find(k);
+    return it == c.end() ? dflt : it->second;
+}
+
+int64_t mat_numel(int kind, int64_t n, int64_t N) {
+    switch (kind) {
+        case OPTI_KF_MAT_NONE: return 0;
+        case OPTI_KF_MAT_DIAG: return n;
+        case OPTI_KF_MAT_DIAG_PER: return n * N;
+        case OPTI_KF_MAT_DENSE: return n * n;
+        case OPTI_KF_MAT_DENSE_PER: return n * n * N;
+        default: TORCH_CHECK(false, "optistate_b200: bad matrix kind ", kind);
+    }
+}
+
+// cfg: integer settings; consts: dt, mass, inertia0..2, gravity; tensors: named device arrays (see optistate_kf.h)
+int kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::string, double> &consts, const TensorMap &tensors) {
+    OptiKfDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = (int32_t)geti(cfg, "dtype", OPTI_KF_F64);
+    d.algo = (int32_t)geti(cfg, "algo", OPTI_KF_ALGO_AUTO);
+    d.cov_model = (int32_t)geti(cfg, "cov_model", OPTI_KF_COV_PREDICT);
+    d.phases = (int32_t)geti(cfg, "phases", OPTI_KF_PHASE_ALL);
+    d.n_traj = geti(cfg, "n_traj", 0);
+    d.n_steps = geti(cfg, "n_steps", 0);
+    d.n_streams = geti(cfg, "n_streams", 0);
+    d.stream_offset = geti(cfg, "stream_offset", 0);
+    d.x0_per_traj = (int32_t)geti(cfg, "x0_per_traj", 0);
+    d.p0_kind = (int32_t)geti(cfg, "p0_kind", OPTI_KF_MAT_NONE);
+    d.q_kind = (int32_t)geti(cfg, "q_kind", OPTI_KF_MAT_DIAG);
+    d.r_kind = (int32_t)geti(cfg, "r_kind", OPTI_KF_MAT_DIAG);
+    d.ckpt_every = geti(cfg, "ckpt_every", 0);
+    d.dt = consts.at("dt");
+    d.mass = consts.at("mass");
+    d.inertia[0] = consts.at("inertia0");
+    d.inertia[1] = consts.at("inertia1");
+    d.inertia[2] = consts.at("inertia2");
+    d.gravity = consts.at("gravity");
+    TORCH_CHECK(d.dtype == OPTI_KF_F64 || d.dtype == OPTI_KF_F32, "optistate_b200: bad dtype");
+    TORCH_CHECK(d.n_traj >= 0 && d.n_steps >= 0 && d.n_streams > 0, "optistate_b200: bad sizes");
+    auto x0 = tensors.find("x0");
+    TORCH_CHECK(x0 != tensors.end() && x0->second.is_cuda(), "optistate_b200: 'x0' must be a CUDA tensor (there is no CPU path)");
+    const Checker ck{d.dtype == OPTI_KF_F64 ? at::kDouble : at::kFloat, x0->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    const int64_t N = d.n_traj, T = d.n_steps, S = d.n_streams;
+    const bool m = d.phases & OPTI_KF_PHASE_MEASURE, p = d.phases & OPTI_KF_PHASE_PREDICT, u = d.phases & OPTI_KF_PHASE_UPDATE;
+    d.imu = ck.get(tensors, "imu", T * 6 * S, m);
+    d.p = ck.get(tensors, "p", T * 12 * S, m || p);
+    d.dp = ck.get(tensors, "dp", T * 12 * S, m);
+    d.contact = ck.get(tensors, "contact", T * 4 * S, m);
+    d.f = ck.get(tensors, "f", T * 12 * S, p);
+    d.z_in = ck.get(tensors, "z_in", T * 10 * S, u && !m);
+    d.body_ref = ck.get(tensors, "body_ref", T * 12 * S, p && d.cov_model == OPTI_KF_COV_MPC);
+    d.truth = ck.get(tensors, "truth", T * 12 * S, false);
+    d.nominal = ck.get(tensors, "nominal", T * 12 * S, false);
+    d.x0 = ck.get(tensors, "x0", d.x0_per_traj ? 12 * N : 12, true);
+    d.P0 = ck.get(tensors, "P0", mat_numel(d.p0_kind, 12, N), d.p0_kind != OPTI_KF_MAT_NONE);
+    d.Q = ck.get(tensors, "Q", mat_numel(d.q_kind, 12, N), true);
+    d.R = ck.get(tensors, "R", mat_numel(d.r_kind, 10, N), true);
+    {
+        auto it = tensors.find("stream_index");
+        if (it != tensors.end()) {
+            const at::Tensor &t = it->second;
+            TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == N,
+                        "optistate_b200: 'stream_index' must be a contiguous int32 CUDA tensor of N elements");
+            d.stream_index = t.data_ptr<int32_t>();
+        }
+        auto is = tensors.find("status");
+        if (is != tensors.end()) {
+            const at::Tensor &t = is->second;
+            TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == N,
+                        "optistate_b200: 'status' must be a contiguous int32 CUDA tensor of N elements");
+            d.status = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+        }
+    }
+    const int64_t n_ckpt = d.ckpt_every > 0 ? T / d.ckpt_every : 0;
+    d.x_steps = const_cast<void *>(ck.get(tensors, "x_steps", T * 12 * N, false));
+    d.x_model_steps = const_cast<void *>(ck.get(tensors, "x_model_steps", T * 12 * N, false));
+    d.p_world_steps = const_cast<void *>(ck.get(tensors, "p_world_steps", T * 12 * N, false));
+    d.z_steps = const_cast<void *>(ck.get(tensors, "z_steps", T * 10 * N, false));
+    d.p_trace_steps = const_cast<void *>(ck.get(tensors, "p_trace_steps", T * N, false));
+    d.k_gain_steps = const_cast<void *>(ck.get(tensors, "k_gain_steps", T * N, false));
+    d.nis_steps = const_cast<void *>(ck.get(tensors, "nis_steps", T * N, false));
+    d.P_ckpt = const_cast<void *>(ck.get(tensors, "P_ckpt", n_ckpt * 144 * N, false));
+    d.x_final = const_cast<void *>(ck.get(tensors, "x_final", 12 * N, false));
+    d.P_final = const_cast<void *>(ck.get(tensors, "P_final", 144 * N, false));
+    d.K_final = const_cast<void *>(ck.get(tensors, "K_final", 120 * N, false));
+    d.summary = const_cast<void *>(ck.get(tensors, "summary", (int64_t)OPTI_KF_SUMMARY_ROWS * N, false));
+    return optistate_kf_batch(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
+int kf_resolve_algo(const std::map<std::string, int64_t> &cfg) {
+    // shape-free query: only kinds / phases / model matter, pointers are faked as non-null
+    OptiKfDesc d;
+    std::memset(&d, 0, sizeof d);
+    static const double dummy = 0.0;
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = (int32_t)geti(cfg, "dtype", OPTI_KF_F64);
+    d.algo = (int32_t)geti(cfg, "algo", OPTI_KF_ALGO_AUTO);
+    d.cov_model = (int32_t)geti(cfg, "cov_model", OPTI_KF_COV_PREDICT);
+    d.phases = (int32_t)geti(cfg, "phases", OPTI_KF_PHASE_ALL);
+    d.n_traj = 1; d.n_steps = 1; d.n_streams = 1;
+    d.p0_kind = (int32_t)geti(cfg, "p0_kind", OPTI_KF_MAT_NONE);
+    d.q_kind = (int32_t)geti(cfg, "q_kind", OPTI_KF_MAT_DIAG);
+    d.r_kind = (int32_t)geti(cfg, "r_kind", OPTI_KF_MAT_DIAG);
+    d.dt = 0.01; d.mass = 1; d.inertia[0] = d.inertia[1] = d.inertia[2] = 1;
+    d.imu = d.p = d.dp = d.contact = d.f = d.z_in = d.body_ref = d.x0 = d.P0 = d.Q = d.R = &dummy;
+    if (geti(cfg, "want_K", 0)) d.K_final = const_cast<double *>(&dummy);
+    return optistate_kf_resolve_algo(&d);
+}
+
+int kf_measure(int64_t dtype, int64_t n_steps, int64_t n_streams, const TensorMap &tensors) {
+    OptiKfMeasureDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = (int32_t)dtype;
+    d.n_steps = n_steps;
+    d.n_streams = n_streams;
+    auto imu = tensors.find("imu");
+    TORCH_CHECK(imu != tensors.end() && imu->second.is_cuda(), "optistate_b200: 'imu' must be a CUDA tensor (there is no CPU path)");
+    const Checker ck{dtype == OPTI_KF_F64 ? at::kDouble : at::kFloat, imu->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    const int64_t T = n_steps, S = n_streams;
+    d.imu = ck.get(tensors, "imu", T * 6 * S, true);
+    d.p = ck.get(tensors, "p", T * 12 * S, true);
+    d.dp = ck.get(tensors, "dp", T * 12 * S, true);
+    d.contact = ck.get(tensors, "contact", T * 4 * S, true);
+    d.z = const_cast<void *>(ck.get(tensors, "z", T * 10 * S, false));
+    d.odom = const_cast<void *>(ck.get(tensors, "odom", T * 4 * S, false));
+    auto is = tensors.find("status");
+    if (is != tensors.end()) {
+        const at::Tensor &t = is->second;
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == S,
+                    "optistate_b200: 'status' must be a contiguous int32 CUDA tensor of S elements");
+        d.status = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+    }
+    return optistate_kf_measure(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
+std::pair<double, double> fma_peak(int64_t dtype, int64_t fma_per_thread) {
+    double flops = 0, secs = 0;
+    const int rc = optistate_fma_peak((int)dtype, fma_per_thread, &flops, &secs, at::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == 0, "optistate_fma_peak: ", optistate_kf_strerror(rc));
+    return {flops, secs};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "PyTorch loader of liboptistate_kf.so (C ABI in include/optistate_kf.h)";
+    m.def("kf_batch", &kf_batch);
+    m.def("kf_measure", &kf_measure);
+    m.def("kf_resolve_algo", &kf_resolve_algo);
+    m.def("fma_peak", &fma_peak);
+    m.def("strerror", [](int rc) { return std::string(optistate_kf_strerror(rc)); });
+    m.def("launch_count", []() { return optistate_kf_launch_count(); });
+    m.def("abi_version", []() { return optistate_kf_abi_version(); });
+    m.def("desc_size", []() { return (int64_t)optistate_kf_desc_size(); });
+    m.attr("SUMMARY_ROWS") = (int)OPTI_KF_SUMMARY_ROWS;
+}

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: trajectories are independent, so they are sharded in contiguous blocks, one block per
+rank (one process per GPU), with NO traffic between GPUs inside the time loop.  The only collective is the
+all-gather of the per-trajectory summaries (and optionally final states) after the loop - NCCL over NVLink /
+NVSwitch on the GPU box, gloo in the CPU tests of this host logic.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) block of trajectories owned by `rank`; the first n_total % world_size ranks get one more."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(n_total), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_total: int, world_size: int):
+    return [shard_range(n_total, world_size, r)[1] - shard_range(n_total, world_size, r)[0] for r in range(world_size)]
+
+
+def gather_columns(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gathers per-trajectory columns: local [C, n_local] on every rank -> [C, n_total] on every rank, in
+    trajectory order.  Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_total, world)
+    if local.shape[-1] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"local shard has {local.shape[-1]} trajectories, expected {sizes[dist.get_rank(group)]}")
+    pad = max(sizes)
+    C = local.shape[0]
+    send = local.new_zeros((pad, C))
+    send[: local.shape[-1]] = local.t()  # trajectory-major rows so that the gathered buffer is one contiguous block per rank
+    recv = local.new_empty((world * pad, C))
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    parts = [recv[r * pad : r * pad + sizes[r]] for r in range(world)]
+    return torch.cat(parts, dim=0).t().contiguous()
+
+
+def kf_batch_sharded(streams: Dict[str, torch.Tensor], n_total: int, *, Q=None, R=None, x0=None, member_offset: int = 0,
+                     gather: bool = True, group=None, **kw):
+    """Filters this rank's contiguous block of `n_total` trajectories and (optionally) all-gathers the summaries.
+
+    streams: dict with imu, p, dp, contact, f (and optional truth, nominal), replicated on every rank ([T, C, S]).
+    Q, R, x0: either shared, or per-trajectory arrays for the LOCAL block ([C, n_local]).
+    Trajectory i (global id) reads stream (i + member_offset) % S, so the shard boundary does not change the mapping.
+    Returns (KfBatchResult of the local block, gathered summary [52, n_total] or None).
+    """
+    from .batch import kf_batch
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    begin, end = shard_range(n_total, world, rank)
+    outputs = tuple(kw.pop("outputs", ("summary",)))
+    if gather and "summary" not in outputs:
+        outputs = outputs + ("summary",)
+    res = kf_batch(streams["imu"], streams["p"], streams["dp"], streams["contact"], streams["f"], x0=x0, Q=Q, R=R,
+                   n_traj=end - begin, stream_offset=begin + member_offset, truth=streams.get("truth"),
+                   nominal=streams.get("nominal"), outputs=outputs, **kw)
+    gathered: Optional[torch.Tensor] = None
+    if gather:
+        gathered = gather_columns(res.summary, n_total, group=group)
+    return res, gathered

@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the PyTorch extension -> C ABI -> sm_100a kernels) against
+(a) the golden vectors minted from the unmodified reference and (b) the C oracle on freshly generated inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, cases
+from optistate_b200 import kf_batch
+from optistate_b200.synth import make_streams
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+ALL_OUT = ("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "P_ckpt", "final")
+DIAG_CASES = ["cfg1_default_seed0", "default_seed11_10k", "stress_qrpkl_seed3_10k", "edge_zero_attitude_spin",
+              "edge_yaw_quarter_turn", "edge_contact_patterns", "edge_large_angles"]
+JOINT_ONLY = ["edge_dense_noise", "edge_nonsymmetric_p0"]
+
+
+def run_case(name, algo, dtype=torch.float64, **kw):
+    stream, ckw, _ = cases.build(name)
+    T = stream["imu"].shape[0]
+    every = 1000 if T >= 2000 else max(T // 4, 1)
+    s = cases.stack_stream(stream)
+    res = kf_batch(s["imu"], s["p"], s["dp"], s["contact"], s["f"], x0=ckw["x0"], P0=ckw["P0"], Q=ckw["Q"], R=ckw["R"],
+                   dtype=dtype, outputs=ALL_OUT, ckpt_every=every, algo=algo,
+                   cov_model="mpc" if ckw["model"] == "mpc_cov" else "predict", body_ref=s.get("body_ref"), **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def compare_golden(name, res, tol_x, tol_p, tol_tr):
+    g = cases.load_golden(name)
+    st = g["steps"]
+    x = res.x_steps[:, :, 0].cpu().numpy().astype(np.float64)
+    errs = {
+        "x": parity.state_err(x[st], g["x"], g["x_absmax"]),
+        "x_model": parity.state_err(res.x_model_steps[:, :, 0].cpu().numpy()[st], g["x_model"], g["x_absmax"]),
+        "z": parity.rel_err(res.z_steps[:, :, 0].cpu().numpy()[st], g["z"]),
+        "p_world": parity.rel_err(res.p_world_steps[:, :, 0].cpu().numpy()[st], g["p_world"]),
+        "p_trace": parity.rel_err(res.p_trace_steps[:, 0].cpu().numpy()[st], g["p_trace"]),
+        "k_gain": parity.rel_err(res.k_gain_steps[:, 0].cpu().numpy()[st], g["k_gain"]),
+    }
+    P_ck = res.P_matrix("P_ckpt")[:, 0].cpu().numpy()
+    errs["P_ckpt"], errs["P_corr"] = parity.cov_err(P_ck, g["P_ckpt"])
+    errs["P_final"] = parity.cov_err(res.P_matrix("P_final")[0].cpu().numpy(), g["P_final"])[0]
+    print(name, res.algo, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k in ("x", "x_model", "z", "p_world"):
+        assert errs[k] < tol_x, (k, errs[k])
+    for k in ("P_ckpt", "P_final"):
+        assert errs[k] < tol_p, (k, errs[k])
+    for k in ("p_trace", "k_gain"):
+        assert errs[k] < tol_tr, (k, errs[k])
+    return errs
+
+
+@pytest.mark.parametrize("name", DIAG_CASES)
+@pytest.mark.parametrize("algo", ["sequential", "joint"])
+def test_fp64_matches_reference_golden(name, algo):
+    """north_star: FP64 within 1e-9 relative on states and covariances."""
+    res = run_case(name, algo)
+    assert res.algo == algo
+    errs = compare_golden(name, res, parity.FP64_TOL, parity.FP64_TOL, parity.FP64_TOL)
+    assert errs["P_corr"] < 1e-7  # entry-scaled covariance error, see tests/parity.py
+    assert int(res.status[0]) == 0
+
+
+@pytest.mark.parametrize("name", JOINT_ONLY)
+def test_fp64_joint_dense_and_nonsymmetric(name):
+    res = run_case(name, "auto")
+    assert res.algo == "joint"  # dense noise / non-symmetric P0 cannot take the packed-symmetric kernel
+    compare_golden(name, res, parity.FP64_TOL, parity.FP64_TOL, parity.FP64_TOL)
+    g = cases.load_golden(name)
+    K = res.tensors.get("K_final")
+    res2 = run_case(name, "joint", )
+    assert torch.equal(res.x_steps, res2.x_steps)  # deterministic
+
+
+def test_fp64_joint_emits_gain_matrix():
+    stream, ckw, _ = cases.build("edge_dense_noise")
+    s = cases.stack_stream(stream)
+    res = kf_batch(s["imu"], s["p"], s["dp"], s["contact"], s["f"], x0=ckw["x0"], P0=ckw["P0"], Q=ckw["Q"], R=ckw["R"],
+                   outputs=("K_final", "x_final"))
+    g = cases.load_golden("edge_dense_noise")
+    K = res.K_final[:, 0].cpu().numpy().reshape(12, 10)
+    assert parity.rel_err(K, g["K_last"]) < parity.FP64_TOL
+
+
+def test_next_row_mpc_covariance_model():
+    """predict_mpc's element-wise exp transition.  cond(S) ~ 6e6 there, so the reference's own
+    P is only defined to ~1e-9 of max|P| (see tests/test_oracle.py); states stay within the north-star bound."""
+    res = run_case("next_mpc_cov_seed5", "auto")
+    assert res.algo == "joint"
+    compare_golden("next_mpc_cov_seed5", res, parity.FP64_TOL, 5e-8, 5e-8)
+
+
+@pytest.mark.parametrize("name", ["default_seed11_10k", "stress_qrpkl_seed3_10k", "cfg1_default_seed0"])
+@pytest.mark.parametrize("algo", ["sequential", "joint"])
+def test_fp32_within_stated_tolerance_over_10k_steps(name, algo):
+    """north_star: FP32 variant within a stated tolerance over 10k-step trajectories:
+    states 2e-5 x per-state max, P 2e-4 x max|P|, P_trace / K_gain 5e-4 relative."""
+    res = run_case(name, algo, dtype=torch.float32)
+    compare_golden(name, res, parity.FP32_TOL_X, parity.FP32_TOL_P, parity.FP32_TOL_TRACE)
+
+
+def test_fp32_truncation_decision_follows_fp64_semantics():
+    """FP32 cos() rounds to 1 for |angle| < 2.4e-4; trunc(R^T) must still only fire where FP64 would."""
+    stream, ckw, _ = cases.build("edge_zero_attitude_spin")
+    s = cases.stack_stream(stream)
+    x0 = ckw["x0"].copy()
+    x0[0:3] = [1e-4, -5e-5, 2e-5]  # FP32 cosines are exactly 1 here, FP64 cosines are not
+    ref = c_oracle.run(s, x0=x0, want=("x_steps",))["x_steps"][:, :, 0]
+    for algo in ("sequential", "joint"):
+        res = kf_batch(s["imu"], s["p"], s["dp"], s["contact"], s["f"], x0=x0, dtype=torch.float32, algo=algo)
+        x = res.x_steps[:, :, 0].cpu().numpy().astype(np.float64)
+        assert parity.state_err(x, ref) < parity.FP32_TOL_X
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-5)])
+def test_batch_of_streams_matches_c_oracle(dtype, tol):
+    """Fresh seeded inputs, many trajectories: per-trajectory streams, shared streams with Monte-Carlo noise,
+    explicit stream_index, per-trajectory x0."""
+    from optistate_b200.synth import monte_carlo_noise
+
+    S, T, N = 24, 300, 96
+    st = make_streams(range(100, 100 + S), T)
+    q, r = monte_carlo_noise(np.arange(N), np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT), nominal_every=S)
+    rng = np.random.default_rng(5)
+    x0 = cases.START[:, None] + 0.01 * rng.standard_normal((12, N))
+    idx = rng.integers(0, S, N).astype(np.int32)
+    ref = c_oracle.run(st, N, Q=q, R=r, x0=x0, stream_index=idx, want=("x_steps", "p_trace_steps", "k_gain_steps", "P_final", "nis_steps"))
+    for algo in ("sequential", "joint"):
+        res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], x0=x0, Q=q, R=r, n_traj=N, stream_index=idx,
+                       dtype=dtype, algo=algo, outputs=("x_steps", "p_trace", "k_gain", "P_final", "nis"))
+        x = res.x_steps.cpu().numpy().astype(np.float64)
+        scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
+        assert (np.abs(x - ref["x_steps"]).max(axis=(0, 2)) / scale).max() < tol
+        assert parity.rel_err(res.p_trace_steps.cpu().numpy(), ref["p_trace_steps"]) < 10 * tol
+        assert parity.rel_err(res.k_gain_steps.cpu().numpy(), ref["k_gain_steps"]) < 10 * tol
+        assert parity.rel_err(res.nis_steps.cpu().numpy(), ref["nis_steps"]) < 100 * tol
+        assert parity.rel_err(res.P_final.cpu().numpy(), ref["P_final"]) < 10 * tol
+        assert int(res.status.max()) == 0
+    # modular stream mapping with an offset
+    ref2 = c_oracle.run(st, N, Q=q, R=r, stream_index=((np.arange(N) + 5) % S).astype(np.int32), want=("x_final",))
+    res2 = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], Q=q, R=r, n_traj=N, stream_offset=5, dtype=dtype,
+                    outputs=("x_final",))
+    assert parity.rel_err(res2.x_final.cpu().numpy(), ref2["x_final"]) < 10 * tol
+
+
+def test_preformed_measurements_and_measure_kernel():
+    from optistate_b200 import kf_measure
+
+    st = make_streams(range(7), 128)
+    z, status = kf_measure(st["imu"], st["p"], st["dp"], st["contact"])
+    ref = c_oracle.run(st, want=("z_steps", "x_steps"))
+    assert parity.rel_err(z.cpu().numpy(), ref["z_steps"]) < 1e-13
+    res = kf_batch(None, st["p"], None, None, st["f"], z=z, outputs=("x_steps",))
+    assert res.algo == "sequential"
+    assert parity.rel_err(res.x_steps.cpu().numpy(), ref["x_steps"]) < 1e-10
+    assert int(status.max()) == 0
+
+
+def test_status_bits_all_swing_and_not_pd():
+    st = make_streams(range(4), 50)
+    st["contact"][10, :, 2] = 0.0
+    res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], outputs=("x_final",))
+    status = res.status.cpu().numpy()
+    assert status[2] & 4 and not (status[[0, 1, 3]] & 4).any()
+    ref = c_oracle.run(st, want=("x_final",))
+    assert (ref["status"] & 4).tolist() == (status & 4).tolist()
+    assert parity.rel_err(res.x_final.cpu().numpy(), ref["x_final"]) < 1e-9
+    # negative measurement noise that drives a pivot non-positive
+    r_bad = np.full(10, 0.01)
+    r_bad[3] = -1.0
+    for algo in ("sequential", "joint"):
+        res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], R=r_bad, algo=algo, outputs=("x_final",))
+        assert (res.status.cpu().numpy() & 1).all()
+
+
+def test_summary_rows():
+    from optistate_b200.batch import SUMMARY_FIELDS
+
+    S, T, N = 8, 400, 32
+    st = make_streams(range(40, 40 + S), T)
+    nominal = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], outputs=("x_steps",)).x_steps
+    from optistate_b200.synth import monte_carlo_noise
+
+    q, r = monte_carlo_noise(np.arange(N), np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT), nominal_every=S)
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 1e-4)):
+        res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], Q=q, R=r, n_traj=N, dtype=dtype,
+                       truth=st["truth"], nominal=nominal.to(dtype), outputs=("summary", "x_steps", "nis", "final", "p_trace", "k_gain"))
+        sm = res.summary.cpu().numpy().astype(np.float64)
+        x = res.x_steps.cpu().numpy().astype(np.float64)
+        idx = np.arange(N) % S
+        truth = st["truth"][:, :, idx]
+        nom = nominal.cpu().numpy()[:, :, idx]
+        assert np.allclose(sm[SUMMARY_FIELDS["x_final"]], x[-1], rtol=0, atol=0)
+        assert np.allclose(sm[SUMMARY_FIELDS["rmse_truth"]], np.sqrt(((x - truth) ** 2).mean(axis=0)), rtol=tol * 10, atol=1e-12)
+        assert np.allclose(sm[SUMMARY_FIELDS["rms_dev_nominal"]], np.sqrt(((x - nom) ** 2).mean(axis=0)), rtol=1e-3, atol=1e-5 if dtype == torch.float32 else 1e-12)
+        assert np.allclose(sm[SUMMARY_FIELDS["mean_nis"]], res.nis_steps.cpu().numpy().astype(np.float64).mean(axis=0), rtol=1e-5)
+        assert np.allclose(sm[SUMMARY_FIELDS["p_diag"]], res.P_final.cpu().numpy()[::13], rtol=0, atol=0)
+        assert np.allclose(sm[SUMMARY_FIELDS["p_trace"]], res.p_trace_steps[-1].cpu().numpy())
+        assert np.allclose(sm[SUMMARY_FIELDS["k_gain"]], res.k_gain_steps[-1].cpu().numpy())
+        if dtype == torch.float64:  # nominal members (u = v = 0) reproduce the nominal run exactly
+            assert np.abs(sm[SUMMARY_FIELDS["rms_dev_nominal"]][:, :S]).max() == 0.0
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (1,024 trajectories x 10,000 steps, FP64): checked through size-independent
+    properties - the analytic steady state of the directly measured states (scalar Riccati, q = r = 0.01 ->
+    P = 0.0061803...), linear growth of the unobserved x-position variance, chunked resume == one pass, and a
+    sample of trajectories against the C oracle."""
+    S, T = 1024, 10000
+    st = make_streams(range(S), T)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in st.items()}
+    res = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], outputs=("x_steps", "final", "p_trace"))
+    torch.cuda.synchronize()
+    P = res.P_matrix("P_final").cpu().numpy()
+    assert int(res.status.max()) == 0
+    golden_ratio_p = 0.01 * (np.sqrt(5) - 1) / 2
+    assert np.abs(P[:, 0, 0] - 6.1804473556e-03).max() < 1e-9  # SURVEY 8(c) known answer diag(P)[0]
+    assert abs(golden_ratio_p - 6.18034e-3) < 1e-8
+    assert np.abs(P[:, 3, 3] / (0.01 * T) - 1).max() < 2e-3  # unobserved x variance ~ q * T
+    sample = [0, 511, 1023]
+    ref = c_oracle.run({k: np.ascontiguousarray(v[:, :, sample]) for k, v in st.items()}, want=("x_steps", "P_final"))
+    x = res.x_steps[:, :, sample].cpu().numpy()
+    scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
+    assert (np.abs(x - ref["x_steps"]).max(axis=(0, 2)) / scale).max() < 1e-9
+    assert parity.rel_err(res.P_final[:, sample].cpu().numpy(), ref["P_final"]) < 1e-9
+    # resume: two chunks of 5,000 steps chained through (x_final, P_final) reproduce the single pass bit for bit
+    half = T // 2
+    a = kf_batch(dev["imu"][:half], dev["p"][:half], dev["dp"][:half], dev["contact"][:half], dev["f"][:half], outputs=("final",))
+    b = kf_batch(dev["imu"][half:], dev["p"][half:], dev["dp"][half:], dev["contact"][half:], dev["f"][half:],
+                 x0=a.x_final, P0=a.P_final, p0_kind=4, outputs=("final",))
+    assert torch.equal(b.x_final, res.x_final) and torch.equal(b.P_final, res.P_final)
