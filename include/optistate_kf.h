@@ -137,6 +137,12 @@ typedef struct OptiKfDesc {
                              36-47 RMS deviation from nominal, 48 mean NIS, 49 trace P, 50 K gain,
                              51 sqrt(max_t NIS_t)                          */
     uint32_t *status;     /* [N] */
+
+    /* optional scratch (device memory owned by the caller) of at least optistate_kf_workspace_bytes():
+       lets the SEQUENTIAL path hoist the state-independent measurement formation into a pre-pass and stream
+       the per-step inputs with TMA; without it the measurement is formed inside the filter kernel */
+    void *workspace;
+    size_t workspace_bytes;
 } OptiKfDesc;
 
 typedef struct OptiKfMeasureDesc {
@@ -158,7 +164,7 @@ int optistate_kf_batch_f32(const OptiKfDesc *desc, void *cuda_stream);
 int optistate_kf_measure(const OptiKfMeasureDesc *desc, void *cuda_stream);
 /* Which algo optistate_kf_batch would run for this descriptor (OPTI_KF_ALGO_JOINT / _SEQUENTIAL) or an error. */
 int optistate_kf_resolve_algo(const OptiKfDesc *desc);
-/* Scratch memory the call needs: always 0 today (everything lives in registers / shared memory). */
+/* Scratch memory the call can use (0 when it would not be used); see OptiKfDesc.workspace. */
 int optistate_kf_workspace_bytes(const OptiKfDesc *desc, size_t *bytes_out);
 /* FMA-chain micro-benchmark: sustained FLOP/s (2 per FMA) of dependent-free FMA issue on the current device.
  * Synchronises the stream (it has to time the kernel).  seconds_out may be NULL. */

@@ -201,7 +201,16 @@ def kf_batch(
     consts = dict(dt=float(dt), mass=float(mass), inertia0=float(inertia[0]), inertia1=float(inertia[1]),
                   inertia2=float(inertia[2]), gravity=float(gravity))
     with torch.cuda.device(device):
-        nv.check(ext.kf_batch(cfg, consts, tensors), "optistate_kf_batch")
+        # scratch for the streamed SEQUENTIAL path (measurement pre-pass + TMA-fed kernel); 0 bytes when unused
+        ws_bytes = ext.kf_batch(dict(cfg, query_workspace=1), consts, tensors)
+        if ws_bytes < 0:
+            nv.check(int(ws_bytes), "optistate_kf_workspace_bytes")
+        if ws_bytes > 0:
+            ws = out.get("workspace") if out is not None else None
+            if ws is None or ws.numel() < ws_bytes:
+                ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+            tensors["workspace"] = ws
+        nv.check(int(ext.kf_batch(cfg, consts, tensors)), "optistate_kf_batch")
     return KfBatchResult(algo=_ALGO_NAMES[cfg["algo"]], n_traj=N, n_steps=T,
                          tensors={k: tensors[k] for k in want}, status=status)
 

@@ -6,6 +6,7 @@
 
 #include "kf_joint.cuh"
 #include "kf_seq.cuh"
+#include "kf_seq_tma.cuh"
 
 namespace {
 
@@ -79,11 +80,70 @@ okf::Params<Real> make_params(const OptiKfDesc *d) {
 }
 
 template <typename Real>
+void launch_measure(long long T, long long S, const Real *imu, const Real *p, const Real *dp, const Real *contact, Real *z,
+                    Real *odom, uint32_t *status, cudaStream_t stream);
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// bytes of scratch the streamed SEQUENTIAL path wants: z [T][10][S] + per-stream status [S]
+size_t seq_workspace_bytes(const OptiKfDesc *d) {
+    if (d->phases != OPTI_KF_PHASE_ALL) return 0;
+    const size_t esz = d->dtype == OPTI_KF_F64 ? 8 : 4;
+    const size_t z_bytes = ((size_t)d->n_steps * okf::NZ * (size_t)d->n_streams * esz + 255) & ~(size_t)255;
+    return z_bytes + (((size_t)d->n_streams * sizeof(uint32_t) + 255) & ~(size_t)255);
+}
+
+// The streamed kernel needs 128 consecutive trajectories to read 128 consecutive, 16-byte aligned streams.
+bool tma_layout_ok(const OptiKfDesc *d) {
+    if (d->stream_index != nullptr || d->n_steps == 0) return false;
+    if (d->n_streams % okf::TMA_THREADS != 0 || d->stream_offset % okf::TMA_THREADS != 0) return false;
+    if (!aligned16(d->p) || !aligned16(d->f)) return false;
+    if (d->summary && ((d->truth && !aligned16(d->truth)) || (d->nominal && !aligned16(d->nominal)))) return false;
+    return true;
+}
+
+template <typename Real, bool kSummary>
+int launch_seq_tma(const okf::Params<Real> &p, cudaStream_t stream) {
+    const int n_ch = okf::TMA_CH_BASE + (kSummary ? 12 * ((p.truth ? 1 : 0) + (p.nominal ? 1 : 0)) : 0);
+    const size_t smem = okf::TmaSmem<Real>::total(n_ch, kSummary && sizeof(Real) == 8);
+    auto kern = okf::kf_seq_tma_kernel<Real, kSummary>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
+    const unsigned blocks = (unsigned)((p.N + okf::TMA_THREADS - 1) / okf::TMA_THREADS);
+    kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return OPTI_KF_OK;
+}
+
+template <typename Real>
 int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
     if (d->n_traj == 0) return OPTI_KF_OK;
-    const okf::Params<Real> p = make_params<Real>(d);
+    okf::Params<Real> p = make_params<Real>(d);
     cudaGetLastError();
     if (algo == OPTI_KF_ALGO_SEQUENTIAL) {
+        bool streamed = tma_layout_ok(d);
+        if (streamed && d->phases == OPTI_KF_PHASE_ALL) {
+            // hoist the state-independent measurement formation into a pre-pass over the S base streams
+            const size_t need = seq_workspace_bytes(d);
+            if (d->workspace && d->workspace_bytes >= need && aligned16(d->workspace)) {
+                const size_t esz = sizeof(Real);
+                const size_t z_bytes = ((size_t)d->n_steps * okf::NZ * (size_t)d->n_streams * esz + 255) & ~(size_t)255;
+                Real *z = (Real *)d->workspace;
+                uint32_t *sst = (uint32_t *)((unsigned char *)d->workspace + z_bytes);
+                if (cudaMemsetAsync(sst, 0, (size_t)d->n_streams * sizeof(uint32_t), stream) != cudaSuccess) return OPTI_KF_E_CUDA;
+                launch_measure<Real>(d->n_steps, d->n_streams, p.imu, p.p, p.dp, p.contact, z, nullptr, sst, stream);
+                p.z_in = z;
+                p.stream_status = sst;
+            } else {
+                streamed = false;
+            }
+        } else if (streamed && !aligned16(p.z_in)) {
+            streamed = false;
+        }
+        if (streamed) {
+            const int rc = d->summary ? launch_seq_tma<Real, true>(p, stream) : launch_seq_tma<Real, false>(p, stream);
+            if (rc != OPTI_KF_OK) return rc;
+            return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+        }
         constexpr int kThreads = 128;
         const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);
         const size_t smem = (size_t)okf::SEQ_NOISE_ROWS * kThreads * sizeof(Real);
@@ -128,6 +188,15 @@ __global__ void __launch_bounds__(256) kf_measure_kernel(long long T, long long 
         odom[(t * 4 + 3) * S + s] = zz[9];
     }
     if (status && all_swing) atomicOr(status + s, (uint32_t)OPTI_KF_ST_ALL_SWING);
+}
+
+template <typename Real>
+void launch_measure(long long T, long long S, const Real *imu, const Real *p, const Real *dp, const Real *contact, Real *z,
+                    Real *odom, uint32_t *status, cudaStream_t stream) {
+    const long long total = T * S;
+    if (total == 0) return;
+    kf_measure_kernel<Real><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(T, S, imu, p, dp, contact, z, odom, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 // ---- FMA issue-peak micro-benchmark ----------------------------------------------------------------------------
@@ -188,7 +257,9 @@ int optistate_kf_workspace_bytes(const OptiKfDesc *desc, size_t *bytes_out) {
     const int rc = validate(desc);
     if (rc != OPTI_KF_OK) return rc;
     if (!bytes_out) return OPTI_KF_E_NULL;
-    *bytes_out = 0;
+    const int algo = resolve(desc);
+    if (algo < 0) return algo;
+    *bytes_out = (algo == OPTI_KF_ALGO_SEQUENTIAL && tma_layout_ok(desc)) ? seq_workspace_bytes(desc) : 0;
     return OPTI_KF_OK;
 }
 
@@ -220,17 +291,13 @@ int optistate_kf_measure(const OptiKfMeasureDesc *d, void *cuda_stream) {
     const long long total = d->n_steps * d->n_streams;
     if (total == 0) return OPTI_KF_OK;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
     cudaGetLastError();
     if (d->dtype == OPTI_KF_F64)
-        kf_measure_kernel<double><<<blocks, 256, 0, stream>>>(d->n_steps, d->n_streams, (const double *)d->imu, (const double *)d->p,
-                                                              (const double *)d->dp, (const double *)d->contact, (double *)d->z,
-                                                              (double *)d->odom, d->status);
+        launch_measure<double>(d->n_steps, d->n_streams, (const double *)d->imu, (const double *)d->p, (const double *)d->dp,
+                               (const double *)d->contact, (double *)d->z, (double *)d->odom, d->status, stream);
     else
-        kf_measure_kernel<float><<<blocks, 256, 0, stream>>>(d->n_steps, d->n_streams, (const float *)d->imu, (const float *)d->p,
-                                                             (const float *)d->dp, (const float *)d->contact, (float *)d->z,
-                                                             (float *)d->odom, d->status);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+        launch_measure<float>(d->n_steps, d->n_streams, (const float *)d->imu, (const float *)d->p, (const float *)d->dp,
+                              (const float *)d->contact, (float *)d->z, (float *)d->odom, d->status, stream);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 

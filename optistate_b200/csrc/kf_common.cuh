@@ -30,6 +30,7 @@ struct Params {
     long long ckpt_every;
     Real *P_ckpt, *x_final, *P_final, *K_final, *summary;
     uint32_t *status;
+    const uint32_t *stream_status;  // [S] per-stream flags of the measurement pre-pass, OR-ed into status
 };
 
 template <typename Real> __device__ __forceinline__ void sincos_full(Real a, Real &s, Real &c);

@@ -46,12 +46,52 @@ __device__ __noinline__ void joint_update(Real *x, Real *P, const Real *z, const
         y[i] = z[i] - x[sel(i)];
         for (int j = 0; j < NZ; ++j) L[i * NZ + j] = P[sel(i) * NX + sel(j)] + Rn[i * NZ + j];
     }
-    // visible asymmetry of S (a user-supplied non-symmetric P0/Q/R): the factorisation reads the lower triangle
+    // Visible asymmetry of S (a user-supplied non-symmetric P0 / Q / R; rounding-level asymmetry is ~1e-16): a
+    // Cholesky factorisation would silently symmetrise it, so that rare case takes the pivoted-LU inverse the
+    // reference itself uses (np.linalg.inv, kalman_filter.py:168) and is flagged in the status word.
+    bool asym = false;
     for (int i = 0; i < NZ; ++i)
         for (int j = 0; j < i; ++j) {
             const Real d = fabs(L[i * NZ + j] - L[j * NZ + i]);
-            if (d > Real(1e-6) * sqrt(fabs(L[i * NZ + i] * L[j * NZ + j]))) status |= OPTI_KF_ST_ASYMMETRIC;
+            if (d > Real(sizeof(Real) == 8 ? 1e-12 : 1e-5) * sqrt(fabs(L[i * NZ + i] * L[j * NZ + j]))) asym = true;
         }
+    if (asym) {
+        status |= OPTI_KF_ST_ASYMMETRIC;
+        Real A[NZ * 2 * NZ];  // [S | I] -> Gauss-Jordan with partial pivoting -> [U | L^-1 P], then back substitution
+        for (int i = 0; i < NZ; ++i)
+            for (int j = 0; j < NZ; ++j) { A[i * 2 * NZ + j] = L[i * NZ + j]; A[i * 2 * NZ + NZ + j] = (i == j) ? Real(1) : Real(0); }
+        for (int c = 0; c < NZ; ++c) {
+            int piv = c;
+            for (int rr = c + 1; rr < NZ; ++rr)
+                if (fabs(A[rr * 2 * NZ + c]) > fabs(A[piv * 2 * NZ + c])) piv = rr;
+            if (A[piv * 2 * NZ + c] == Real(0) || !isfinite(A[piv * 2 * NZ + c])) status |= OPTI_KF_ST_NOT_PD;
+            if (piv != c)
+                for (int j = 0; j < 2 * NZ; ++j) { const Real tmp = A[c * 2 * NZ + j]; A[c * 2 * NZ + j] = A[piv * 2 * NZ + j]; A[piv * 2 * NZ + j] = tmp; }
+            for (int rr = c + 1; rr < NZ; ++rr) {
+                const Real m = A[rr * 2 * NZ + c] / A[c * 2 * NZ + c];
+                for (int j = c; j < 2 * NZ; ++j) A[rr * 2 * NZ + j] -= m * A[c * 2 * NZ + j];
+            }
+        }
+        Real *Sinv = L;  // S itself is no longer needed
+        for (int c = NZ - 1; c >= 0; --c)
+            for (int j = 0; j < NZ; ++j) {
+                Real s = A[c * 2 * NZ + NZ + j];
+                for (int k = c + 1; k < NZ; ++k) s -= A[c * 2 * NZ + k] * Sinv[k * NZ + j];
+                Sinv[c * NZ + j] = s / A[c * 2 * NZ + c];
+            }
+        nis = Real(0);
+        for (int i = 0; i < NZ; ++i) {
+            Real s = Real(0);
+            for (int j = 0; j < NZ; ++j) s += Sinv[i * NZ + j] * y[j];
+            nis += y[i] * s;
+        }
+        for (int i = 0; i < NX; ++i)
+            for (int j = 0; j < NZ; ++j) {
+                Real s = Real(0);
+                for (int k = 0; k < NZ; ++k) s += P[i * NX + sel(k)] * Sinv[k * NZ + j];
+                K[i * NZ + j] = s;
+            }
+    } else {
     // Cholesky, in place in the lower triangle; Linv_d[j] = 1 / L[j][j]
     Real dinv[NZ];
     for (int j = 0; j < NZ; ++j) {
@@ -92,6 +132,7 @@ __device__ __noinline__ void joint_update(Real *x, Real *P, const Real *z, const
             K[i * NZ + j] = s * dinv[j];
         }
     }
+    }  // Cholesky path
     for (int i = 0; i < NX; ++i) {
         Real s = Real(0);
         for (int j = 0; j < NZ; ++j) s += K[i * NZ + j] * y[j];

@@ -51,7 +51,7 @@ int64_t mat_numel(int kind, int64_t n, int64_t N) {
 }
 
 // cfg: integer settings; consts: dt, mass, inertia0..2, gravity; tensors: named device arrays (see optistate_kf.h)
-int kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::string, double> &consts, const TensorMap &tensors) {
+int64_t kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::string, double> &consts, const TensorMap &tensors) {
     OptiKfDesc d;
     std::memset(&d, 0, sizeof d);
     d.struct_size = sizeof d;
@@ -125,6 +125,21 @@ int kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::stri
     d.P_final = const_cast<void *>(ck.get(tensors, "P_final", 144 * N, false));
     d.K_final = const_cast<void *>(ck.get(tensors, "K_final", 120 * N, false));
     d.summary = const_cast<void *>(ck.get(tensors, "summary", (int64_t)OPTI_KF_SUMMARY_ROWS * N, false));
+    {
+        auto iw = tensors.find("workspace");
+        if (iw != tensors.end()) {
+            const at::Tensor &t = iw->second;
+            TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kByte && t.is_contiguous(),
+                        "optistate_b200: 'workspace' must be a contiguous uint8 CUDA tensor");
+            d.workspace = t.data_ptr();
+            d.workspace_bytes = (size_t)t.numel();
+        }
+    }
+    if (geti(cfg, "query_workspace", 0)) {
+        size_t bytes = 0;
+        const int rc = optistate_kf_workspace_bytes(&d, &bytes);
+        return rc < 0 ? rc : (int64_t)bytes;
+    }
     return optistate_kf_batch(&d, at::cuda::getCurrentCUDAStream().stream());
 }
 

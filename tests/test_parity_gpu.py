@@ -70,9 +70,7 @@ def test_fp64_joint_dense_and_nonsymmetric(name):
     res = run_case(name, "auto")
     assert res.algo == "joint"  # dense noise / non-symmetric P0 cannot take the packed-symmetric kernel
     compare_golden(name, res, parity.FP64_TOL, parity.FP64_TOL, parity.FP64_TOL)
-    g = cases.load_golden(name)
-    K = res.tensors.get("K_final")
-    res2 = run_case(name, "joint", )
+    res2 = run_case(name, "joint")
     assert torch.equal(res.x_steps, res2.x_steps)  # deterministic
 
 
@@ -233,3 +231,39 @@ def test_full_size_config2_properties():
     b = kf_batch(dev["imu"][half:], dev["p"][half:], dev["dp"][half:], dev["contact"][half:], dev["f"][half:],
                  x0=a.x_final, P0=a.P_final, p0_kind=4, outputs=("final",))
     assert torch.equal(b.x_final, res.x_final) and torch.equal(b.P_final, res.P_final)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-5)])
+def test_streamed_tma_kernel_matches_oracle_and_direct_kernel(dtype, tol):
+    """S % 128 == 0 and offset % 128 == 0 selects the TMA-fed kernel (measurement pre-pass + cp.async.bulk input
+    pipeline); an explicit stream_index forces the direct-load kernel.  Both must agree with the oracle, with a
+    ragged last block (N % 128 != 0), a stream offset, label streams and every per-step output switched on."""
+    from optistate_b200.synth import monte_carlo_noise
+
+    S, T, N, off = 256, 150, 300, 128
+    st = make_streams(range(300, 300 + S), T)
+    q, r = monte_carlo_noise(np.arange(N), np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT))
+    idx = ((np.arange(N) + off) % S).astype(np.int32)
+    ref = c_oracle.run(st, N, Q=q, R=r, stream_index=idx,
+                       want=("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "nis_steps", "P_final", "P_ckpt"), ckpt_every=50)
+    outs = ("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace", "k_gain", "nis", "P_final", "P_ckpt", "summary")
+    kw = dict(Q=q, R=r, n_traj=N, dtype=dtype, outputs=outs, ckpt_every=50, truth=st["truth"], nominal=st["truth"] * 0.5)
+    a = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], stream_offset=off, **kw)            # streamed
+    b = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], stream_index=idx, **kw)             # direct
+    assert a.algo == b.algo == "sequential"
+    scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
+    for res in (a, b):
+        x = res.x_steps.cpu().numpy().astype(np.float64)
+        assert (np.abs(x - ref["x_steps"]).max(axis=(0, 2)) / scale).max() < tol
+        for name in ("x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "P_final", "P_ckpt"):
+            assert parity.rel_err(res.tensors[name].cpu().numpy(), ref[name]) < 10 * tol, name
+        assert parity.rel_err(res.nis_steps.cpu().numpy(), ref["nis_steps"]) < 100 * tol
+        assert int(res.status.max()) == 0
+    # the two kernels run the same arithmetic on the same z when the pre-pass and the fused formation agree
+    assert parity.rel_err(a.x_steps.cpu().numpy(), b.x_steps.cpu().numpy()) < (1e-13 if dtype == torch.float64 else 1e-5)
+    assert parity.rel_err(a.summary.cpu().numpy(), b.summary.cpu().numpy()) < (1e-12 if dtype == torch.float64 else 1e-4)
+    # all-swing flag travels from the pre-pass to the per-trajectory status
+    st["contact"][20, :, 130] = 0.0
+    c = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], n_traj=N, dtype=dtype, outputs=("x_final",))
+    flags = c.status.cpu().numpy() & 4
+    assert flags[130] and flags.sum() // 4 == 1 + (1 if 130 + S < N else 0)
