@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: Kalman-filter trajectory-steps/sec on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--dtype f64|f32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload): the Monte-Carlo noise sweep of BASELINE.json configs[2]/[3] - 1,048,576 trajectories
+x 1,000 steps PER GPU over 1,024 shared synthetic base streams, per-member diagonal Q/R perturbations, outputs =
+per-trajectory summaries (final x, diag P, RMSE vs the label stream, RMS deviation from the nominal member, mean
+NIS, ...) - run in FP64 by default because the north-star target is stated on the FP64 FMA roofline with 1e-9
+parity (--dtype f32 gives configs[2] verbatim).  One "step" of the bench = one full pass of the hot path over
+that batch: measurement pre-pass + the filter kernel (+ the NCCL all-gather of the summaries when N > 1).
+
+  value      whole-job trajectory-steps/s, inputs resident in HBM, timed with CUDA events, max over ranks
+  e2e        same through the public kf_batch() call with pinned HOST buffers: H2D of streams + per-member noise
+             and D2H of the summaries inside the timed region
+  roofline   FMA roofline: achieved = 6,800 algorithmic flops/step x steps/s; peak = FP64 (FP32)
+             FMA issue peak MEASURED in this run by optistate_fma_peak; executed-flop figures alongside
+  cpu_baseline  the oracle's C port of the reference filter on this box's host cores, bounded sample
+
+--impl reference times the CPU arm (oracle C port, all host threads) on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_ALGORITHMIC = 6800.0  # per trajectory-step, reference operand order, structural zeros skipped
+# flops the streamed SEQUENTIAL kernel actually executes per trajectory-step, counted from the SASS of its time loop
+# with ncu (profiles/r1_*): FP64 1110 DFMA + 321 DMUL + 76 DADD ; FP32 see DESIGN.md
+FLOPS_EXECUTED = {"f64": 2 * 1110 + 321 + 76, "f32": 2 * 1119 + 321 + 108}
+METRIC = "kf_trajectory_steps_per_sec"
+UNIT = "trajectory-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--traj-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--streams", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {
+        "workload": f"monte-carlo noise sweep: {a.traj_per_gpu} trajectories x {a.T} steps per GPU, {a.streams} shared base "
+                    f"streams, per-member diagonal Q/R, summary outputs (BASELINE configs[2]/[3] shape, {a.dtype})",
+        "trajectories_per_gpu": a.traj_per_gpu, "trajectories_total": a.traj_per_gpu * world, "steps_per_trajectory": a.T,
+        "base_streams": a.streams, "sharding": f"contiguous blocks x{world}, all-gather of summaries" if world > 1 else "single GPU",
+        "l2": "no explicit flush: per-iteration inputs (streams + per-member noise) exceed the 126 MB L2",
+    }
+
+
+Q_DIAG = np.array([0.01, 0.01, 0.01, 0.01, 0.0001, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.0001])  # settings.py:28
+R_DIAG = np.full(10, 0.01)  # settings.py:30
+BLOCK = 1 << 16
+
+
+def mc_noise(first_member: int, count: int, n_streams: int):
+    """Vectorised Monte-Carlo noise (same law as synth.monte_carlo_noise: 10**U(-0.5,0.5) per diagonal entry; the first
+    pass over the streams stays nominal).  Drawn in blocks of 65,536 members so it is a function of the member id."""
+    q = np.empty((12, count))
+    r = np.empty((10, count))
+    done = 0
+    while done < count:
+        m = first_member + done
+        blk, off = divmod(m, BLOCK)
+        n = min(BLOCK - off, count - done)
+        rng = np.random.default_rng([10**6, blk])
+        u = rng.uniform(-0.5, 0.5, (BLOCK, 22))[off:off + n]
+        q[:, done:done + n] = (Q_DIAG[None, :] * 10.0 ** u[:, :12]).T
+        r[:, done:done + n] = (R_DIAG[None, :] * 10.0 ** u[:, 12:]).T
+        done += n
+    ids = first_member + np.arange(count)
+    nominal = ids < n_streams
+    q[:, nominal] = Q_DIAG[:, None]
+    r[:, nominal] = R_DIAG[:, None]
+    return q, r
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(a, seconds_target=12.0, n_threads=0):
+    """The oracle's C port of the reference filter (oracle/kf_oracle.c) on a bounded sample of the same workload:
+    n_sample trajectories x T steps over the same base streams with Monte-Carlo noise.  Returns (steps/s, dict)."""
+    from oracle import c_oracle
+    from optistate_b200.synth import make_streams
+
+    threads = n_threads or c_oracle.max_threads()
+    S = min(a.streams, 64)
+    st = make_streams(range(S), a.T)
+    q, r = mc_noise(0, threads, S)
+    t0 = time.perf_counter()
+    c_oracle.run(st, threads, Q=q, R=r, n_threads=threads, want=("x_final",))  # calibration: one trajectory per thread
+    dt = time.perf_counter() - t0
+    per_thread = max(1, int(seconds_target / max(dt, 1e-3)))
+    n = threads * min(per_thread, 64)
+    q, r = mc_noise(0, n, S)
+    t0 = time.perf_counter()
+    c_oracle.run(st, n, Q=q, R=r, n_threads=threads, want=("x_final",))
+    dt = time.perf_counter() - t0
+    return n * a.T / dt, {"cores": threads, "kind": "port", "sample": f"{n} trajectories x {a.T} steps ({dt:.1f} s), C port of the reference filter "
+                          f"(oracle/kf_oracle.c, pthreads, one block of trajectories per thread)"}
+
+
+def numpy_port_rate(steps=400):
+    """Interpreter-bound NumPy restatement (what the reference's own loop costs per step, one core)."""
+    from oracle import kf_numpy
+    from optistate_b200.synth import make_stream
+
+    s = make_stream(0, steps)
+    t0 = time.perf_counter()
+    kf_numpy.run(s)
+    return steps / (time.perf_counter() - t0)
+
+
+def run_reference(a):
+    """CPU arm: oracle C port with all host threads; a step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    from optistate_b200.synth import make_streams
+
+    threads = c_oracle.max_threads()
+    S = min(a.streams, 64)
+    st = make_streams(range(S), a.T)
+    n = threads * 16
+    q, r = mc_noise(0, n, S)
+    fn = lambda: c_oracle.run(st, n, Q=q, R=r, n_threads=threads, want=("x_final",))  # noqa: E731
+    t0 = time.perf_counter()
+    fn()
+    first = time.perf_counter() - t0
+    if first * (a.steps + a.warmup) > 240:  # keep the whole arm within a few minutes
+        n = max(threads, int(n * 240 / (first * (a.steps + a.warmup))))
+        q, r = mc_noise(0, n, S)
+    for _ in range(max(a.warmup - 1, 0)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = n * a.T * a.steps / dt
+    sample = f"{n} trajectories x {a.T} steps per step over {S} base streams, Monte-Carlo Q/R"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "numpy_port_steps_per_s_1core": numpy_port_rate()}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+
+    from optistate_b200 import fma_peak, kf_batch
+    from optistate_b200 import _native as nv
+    from optistate_b200.distributed import gather_columns
+    from optistate_b200.synth import make_streams
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float64 if a.dtype == "f64" else torch.float32
+    esz = 8 if a.dtype == "f64" else 4
+    n_local, T, S = a.traj_per_gpu, a.T, a.streams
+    n_total = n_local * world
+    first = rank * n_local
+
+    # ---- synthetic inputs (host, pinned) -------------------------------------------------------------------
+    st = make_streams(range(S), T)
+    host = {k: torch.from_numpy(st[k]).to(dtype).pin_memory() for k in ("imu", "p", "dp", "contact", "f", "truth")}
+    q_np, r_np = mc_noise(first, n_local, S)
+    host["Q"] = torch.from_numpy(q_np).to(dtype).pin_memory()
+    host["R"] = torch.from_numpy(r_np).to(dtype).pin_memory()
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    # label stream 2: the nominal member of every stream (u = v = 0), one small launch, untimed
+    nominal = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], dtype=dtype, outputs=("x_steps",)).x_steps
+    host["nominal"] = nominal.cpu().pin_memory()
+    d["nominal"] = nominal
+    out = {"summary": torch.empty((nv.SUMMARY_ROWS, n_local), dtype=dtype, device=dev),
+           "status": torch.zeros(n_local, dtype=torch.int32, device=dev),
+           "workspace": torch.empty(T * 10 * S * esz + 4 * S + 4096, dtype=torch.uint8, device=dev)}
+    summary_host = torch.empty((nv.SUMMARY_ROWS, n_local), dtype=dtype).pin_memory()
+
+    def step_resident():
+        res = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], Q=d["Q"], R=d["R"], n_traj=n_local, dtype=dtype,
+                       stream_offset=first, truth=d["truth"], nominal=d["nominal"], outputs=("summary",), out=out,
+                       q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER)
+        if world > 1:
+            return gather_columns(res.summary, n_total)
+        return res.summary
+
+    def step_e2e():
+        dd = {k: host[k].to(dev, non_blocking=True) for k in ("imu", "p", "dp", "contact", "f", "truth", "nominal", "Q", "R")}
+        res = kf_batch(dd["imu"], dd["p"], dd["dp"], dd["contact"], dd["f"], Q=dd["Q"], R=dd["R"], n_traj=n_local, dtype=dtype,
+                       stream_offset=first, truth=dd["truth"], nominal=dd["nominal"], outputs=("summary",), out=out,
+                       q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER)
+        summary_host.copy_(res.summary, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(summary_host[48, 0])  # the step's result is read on the host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = nv.ext().launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), nv.ext().launch_count() - l0
+
+    # ---- measured FMA peaks (roofline denominators) --------------------------------------------------------
+    peak_flops, _ = fma_peak(dtype, 1 << 18)
+    for _ in range(a.warmup):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms, launches = timed(step_resident, a.steps)
+    steps_total = n_total * T * a.steps
+    value = steps_total / (ms * 1e-3)
+    status_bad = int((out["status"] != 0).sum().item())
+
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(max(1, a.warmup - 1)):
+            step_e2e()
+        ms_e, _ = timed(step_e2e, a.steps)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("imu", "p", "dp", "contact", "f", "truth", "nominal", "Q", "R"))
+        e2e = {"value": steps_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": summary_host.numel() * summary_host.element_size() * world, "ms_per_step": ms_e / a.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    clocks = clk.summary()
+    per_gpu = value / world
+    peak_tf = peak_flops / 1e12
+    sm_max = clocks.get("sm_max_mhz") or 1965.0
+    lanes = 64 if a.dtype == "f64" else 128
+    theoretical_tf = 148 * lanes * 2 * sm_max * 1e6 / 1e12
+    achieved_tf = per_gpu * FLOPS_ALGORITHMIC / 1e12
+    executed_tf = per_gpu * FLOPS_EXECUTED[a.dtype] / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
+        "data": "synthetic", "config": workload_config(a, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {
+            "bound": "fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+            "note": f"per GPU; achieved = {int(FLOPS_ALGORITHMIC)} algorithmic flops/trajectory-step x steps/s; peak = {a.dtype} FMA issue peak "
+                    "measured in this run (optistate_fma_peak); the kernel executes fewer flops than the algorithmic count "
+                    "(sequential scalar updates on a packed symmetric P), hence frac can exceed 1 - see executed_*",
+            "executed_flops_per_step": FLOPS_EXECUTED[a.dtype], "executed_tflops": executed_tf, "executed_frac_of_measured_peak": executed_tf / peak_tf,
+            "theoretical_peak_tflops": theoretical_tf, "frac_of_theoretical": achieved_tf / theoretical_tf,
+            "hbm_peak_gbs": _hbm_peak(),
+        },
+        "status_nonzero_trajectories": status_bad,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        v, info = cpu_port_rate(a)
+        line["cpu_baseline"] = dict({"value": v, "unit": UNIT}, **info)
+        line["cpu_baseline"]["numpy_port_steps_per_s_1core"] = numpy_port_rate()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0  # B200_PROFILING.md fallback
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
