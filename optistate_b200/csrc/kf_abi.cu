@@ -104,8 +104,8 @@ bool tma_layout_ok(const OptiKfDesc *d) {
 
 template <typename Real, bool kSummary>
 int launch_seq_tma(const okf::Params<Real> &p, cudaStream_t stream) {
-    const int n_ch = okf::TMA_CH_BASE + (kSummary ? 12 * ((p.truth ? 1 : 0) + (p.nominal ? 1 : 0)) : 0);
-    const size_t smem = okf::TmaSmem<Real>::total(n_ch, kSummary && sizeof(Real) == 8);
+    const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
+    const size_t smem = okf::TmaSmem<Real>::total(n_lab, kSummary && sizeof(Real) == 8);
     auto kern = okf::kf_seq_tma_kernel<Real, kSummary>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     const unsigned blocks = (unsigned)((p.N + okf::TMA_THREADS - 1) / okf::TMA_THREADS);

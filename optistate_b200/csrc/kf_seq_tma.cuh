@@ -1,18 +1,23 @@
 // Throughput kernel, streamed variant: same arithmetic as kf_seq.cuh (one thread per trajectory, packed symmetric
 // P and x in registers, sequential scalar updates) with the per-step inputs delivered by the TMA engine.
 //
-//   * A block owns 128 consecutive trajectories that read 128 consecutive base streams, so every input channel
-//     of one step is one contiguous 128-element run of the [T][C][S] layout.  Lanes of warp 0 issue one
-//     cp.async.bulk (global -> shared, completion on an mbarrier with complete_tx) per channel: no per-thread
-//     address arithmetic, no LDG in the recursion, no registers tied up by loads in flight.
-//   * Two stages: the copy for step t+2 is issued as soon as every thread has finished reading step t, i.e. a
-//     whole filter step (~3 us) ahead of its use, which hides HBM/L2 latency behind the FMA work even at
-//     8 warps per SM (the FP64 state needs ~250 registers per thread).
+//   * 32 consecutive trajectories (one warp) read 32 consecutive base streams, so every input channel of one
+//     step is one contiguous 32-element run of the [T][C][S] layout.  Each warp runs its OWN input pipeline:
+//     its lanes issue one cp.async.bulk (global -> shared, completion on a warp-private mbarrier with
+//     complete_tx) per channel.  No per-thread address arithmetic, no LDG in the recursion, no registers tied
+//     up by loads in flight, and no block-wide barrier: warps never wait for each other.
+//   * Three channel groups, each single-buffered and refilled for step t+1 the moment the warp has consumed
+//     step t's copy, so the copy has most of a filter step (several microseconds) to land:
+//         G0 = p[12] f[12]      read at the top of the step (mean model)        -> refilled right away
+//         G1 = z[10]            read one by one as the measurements are folded  -> refilled after the last fold
+//         G2 = truth / nominal  label streams of the summary, read at the end   -> refilled right away
 //   * Inputs are consumed straight from shared memory (conflict-free: consecutive threads, consecutive words);
-//     z_j is read when measurement j is folded in, so nothing but x and P stays live across the step.
-//   * Channels per step: p[12] f[12] z[10] (+ truth[12], nominal[12] label streams when the summary wants them);
-//     z comes from the measurement pre-pass (optistate_kf_measure) because it is state-independent and, with
-//     shared base streams, identical for every Monte-Carlo member of a stream.
+//     nothing but x, P and the next step's rotation matrix stays live across the step.
+//   * Latency of the two long dependent chains is hidden behind the independent rank-1 FMAs: the reciprocal of
+//     the NEXT pivot is started as soon as that pivot's entry has been updated, and the sin/cos of the NEXT
+//     step's attitude are started as soon as the last state update is done.
+//   * z comes from the measurement pre-pass (optistate_kf_measure): it is state-independent and, with shared
+//     base streams, identical for every Monte-Carlo member of a stream.
 #pragma once
 
 #include "kf_seq.cuh"
@@ -20,8 +25,10 @@
 namespace okf {
 
 constexpr int TMA_THREADS = 128;
-constexpr int TMA_STAGES = 2;
-constexpr int TMA_CH_BASE = 34;  // p[12] f[12] z[10]
+constexpr int TMA_WARPS = TMA_THREADS / 32;
+constexpr int TMA_CH_G0 = 24, TMA_CH_G1 = 10;
+constexpr int TMA_NOISE_ROWS = 22;  // q[12] r[10]
+constexpr int TMA_ACC_ROWS = 25;    // running sums of the summary: 0-11 truth, 12-23 nominal, 24 NIS
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -48,38 +55,126 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 template <typename Real>
 struct TmaSmem {
-    // byte offsets inside dynamic shared memory, all 128-byte aligned
-    static __host__ __device__ constexpr size_t stage_bytes(int ch) { return (size_t)ch * TMA_THREADS * sizeof(Real); }
-    static __host__ __device__ constexpr size_t off_stage() { return 128; }  // mbarriers live in the first 128 bytes
-    static __host__ __device__ constexpr size_t off_noise(int ch) { return off_stage() + TMA_STAGES * stage_bytes(ch); }
-    static __host__ __device__ constexpr size_t off_acc(int ch) { return off_noise(ch) + (size_t)SEQ_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
-    static __host__ __device__ constexpr size_t total(int ch, bool acc_in_smem) {
-        return off_acc(ch) + (acc_in_smem ? (size_t)25 * TMA_THREADS * sizeof(double) : 0);
+    // byte offsets inside dynamic shared memory; every array is [rows][TMA_THREADS]
+    static __host__ __device__ constexpr size_t rows(int n) { return (size_t)n * TMA_THREADS * sizeof(Real); }
+    static __host__ __device__ constexpr size_t off_g0() { return 128; }  // mbarriers live in the first 128 bytes
+    static __host__ __device__ constexpr size_t off_g1() { return off_g0() + rows(TMA_CH_G0); }
+    static __host__ __device__ constexpr size_t off_g2() { return off_g1() + rows(TMA_CH_G1); }
+    static __host__ __device__ constexpr size_t off_noise(int n_lab) { return off_g2() + rows(12 * n_lab); }
+    static __host__ __device__ constexpr size_t off_acc(int n_lab) { return off_noise(n_lab) + rows(TMA_NOISE_ROWS); }
+    static __host__ __device__ constexpr size_t total(int n_lab, bool acc_in_smem) {
+        return off_acc(n_lab) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * sizeof(double) : 0);
     }
 };
 
-// warp 0: one bulk copy per channel of step t into stage buffer `dst`
-template <typename Real>
-__device__ __forceinline__ void issue_step_loads(const Params<Real> &prm, long long t, long long s0, int n_ch, Real *dst,
-                                                 uint64_t *bar, int lane) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_ch * TMA_THREADS * sizeof(Real)));
+// One warp, one channel group of step t: lane c copies channel c (32 consecutive streams) into the warp's slice.
+//   group 0: p[0..11] f[0..11]   group 1: z[0..9]   group 2: label streams (truth first when both are present)
+template <typename Real, int G>
+__device__ __forceinline__ void issue_group(const Params<Real> &prm, long long t, long long s_warp, int n_ch, Real *dst_warp,
+                                            uint64_t *bar, int lane) {
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_ch * 32 * sizeof(Real)));
     __syncwarp();
-    const Real *lab0 = prm.truth ? prm.truth : prm.nominal;
-    const Real *lab1 = prm.nominal;
+    if (lane < n_ch) {
+        const Real *arr;
+        int C, c;
+        if (G == 0) {
+            arr = lane < 12 ? prm.p : prm.f; C = 12; c = lane < 12 ? lane : lane - 12;
+        } else if (G == 1) {
+            arr = prm.z_in; C = 10; c = lane;
+        } else {
+            const Real *lab0 = prm.truth ? prm.truth : prm.nominal;
+            arr = lane < 12 ? lab0 : prm.nominal; C = 12; c = lane < 12 ? lane : lane - 12;
+        }
+        bulk_g2s(dst_warp + lane * TMA_THREADS, arr + (t * C + c) * prm.S + s_warp, (uint32_t)(32 * sizeof(Real)), bar);
+    }
+}
+
+// Measurement J folded in with the reciprocal of its pivot already available (`inv` = 1 / (P_kk + r_J)).  The entry
+// that becomes the NEXT pivot is updated first and its reciprocal started at once, so that chain (MUFU + Newton
+// steps) runs underneath the 65 remaining independent FMAs of this rank-1 update.  `mid` runs after the state update.
+template <int J, typename Real, typename Mid>
+__device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Real zj, Real rj, Real r_next, Real inv, Real &inv_next,
+                                               Real &nis, uint32_t &status, Mid mid) {
+    constexpr int k = sel(J);
+    constexpr int kn = (J + 1 < NZ) ? sel(J + 1) : -1;
+    if constexpr (kn >= 0) {
+        const Real wn = P[tri(kn, k)] * inv;
+        const Real pnn = P[tri(kn, kn)] - wn * P[tri(kn, k)];
+        P[tri(kn, kn)] = pnn;
+        const Real s = pnn + r_next;
+        if (!(s > Real(0)) || !(s < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
+        inv_next = Real(1) / s;
+    }
+    const Real y = zj - x[k];
+    const Real g = inv * y;
+    nis += y * g;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int ch = lane + 32 * k;
-        if (ch < n_ch) {
-            const Real *arr;
-            int C, c;
-            if (ch < 12) { arr = prm.p; C = 12; c = ch; }
-            else if (ch < 24) { arr = prm.f; C = 12; c = ch - 12; }
-            else if (ch < 34) { arr = prm.z_in; C = 10; c = ch - 24; }
-            else if (ch < 46) { arr = lab0; C = 12; c = ch - 34; }
-            else { arr = lab1; C = 12; c = ch - 46; }
-            bulk_g2s(dst + ch * TMA_THREADS, arr + (t * C + c) * prm.S + s0, (uint32_t)(TMA_THREADS * sizeof(Real)), bar);
+    for (int i = 0; i < NX; ++i) x[i] += P[tri(i, k)] * g;
+    mid();
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        if (i == k) continue;
+        const Real w = P[tri(i, k)] * inv;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            if (j == k || (i == kn && j == kn)) continue;
+            P[tri(i, j)] -= w * P[tri(j, k)];
         }
     }
+    const Real cfac = rj * inv;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
+}
+
+// Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
+template <typename Real>
+__device__ __forceinline__ void propagate_mean_with_R(const Params<Real> &prm, Real (&x)[NX], Real (&p)[12], const Real (&f)[12],
+                                                      const Real (&R)[9], bool any_trunc) {
+    Real tau[3] = {Real(0), Real(0), Real(0)}, fs[3] = {Real(0), Real(0), Real(0)};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const Real a = p[3 * l], b = p[3 * l + 1], c = p[3 * l + 2];
+        const Real pw0 = R[0] * a + R[1] * b + R[2] * c;
+        const Real pw1 = R[3] * a + R[4] * b + R[5] * c;
+        const Real pw2 = R[6] * a + R[7] * b + R[8] * c;
+        p[3 * l] = pw0; p[3 * l + 1] = pw1; p[3 * l + 2] = pw2;
+        const Real f0 = f[3 * l], f1 = f[3 * l + 1], f2 = f[3 * l + 2];
+        tau[0] += pw1 * f2 - pw2 * f1;
+        tau[1] += pw2 * f0 - pw0 * f2;
+        tau[2] += pw0 * f1 - pw1 * f0;
+        fs[0] += f0; fs[1] += f1; fs[2] += f2;
+    }
+    Real u[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[k] = (R[k] * tau[0] + R[3 + k] * tau[1] + R[6 + k] * tau[2]) * prm.inv_inertia[k];
+    Real dth[3] = {Real(0), Real(0), Real(0)};
+    if (any_trunc) {  // rare: an entry of R is exactly +-1 (axis-aligned attitude); see trunc_rt
+        Real Tm[9];
+        bool any;
+        trunc_rt(R, x, Tm, any);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dth[i] = prm.dt * (Tm[3 * i] * x[6] + Tm[3 * i + 1] * x[7] + Tm[3 * i + 2] * x[8]);
+    }
+    Real xn[NX];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        xn[i] = x[i] + dth[i];
+        xn[3 + i] = x[3 + i] + prm.dt * x[9 + i];
+        xn[6 + i] = x[6 + i] + prm.dt * (R[3 * i] * u[0] + R[3 * i + 1] * u[1] + R[3 * i + 2] * u[2]);
+        xn[9 + i] = x[9 + i] + prm.dt_over_m * fs[i];
+    }
+    xn[11] += prm.dt_g;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+}
+
+// cheap test whether trunc(R^T) can have a non-zero entry (then the exact decision is taken in trunc_rt)
+template <typename Real>
+__device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
+    Real m = Real(0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m = fmax(m, fabs(R[k]));
+    return m >= (sizeof(Real) == 8 ? Real(1) : Real(1.0f - 9.5367431640625e-7f));
 }
 
 template <typename Real, bool kSummary>
@@ -93,36 +188,35 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     const long long i = i0 + tid;
     const bool active = i < N;
     const long long ic = active ? i : N - 1;  // clamped index for per-trajectory parameter loads
-    const long long s0 = (i0 + prm.stream_offset) % S;
-    const int n_lab = (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0);
-    const int n_ch = TMA_CH_BASE + (kSummary ? 12 * n_lab : 0);
+    const long long s_warp = (i0 + prm.stream_offset) % S + 32 * warp;
+    const int n_lab = kSummary ? (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0) : 0;
 
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    Real *stage = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_stage());
-    Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_ch));
-    double *acc_s = reinterpret_cast<double *>(smem_raw + TmaSmem<Real>::off_acc(n_ch)) + tid;
-    const int stage_elems = n_ch * nt;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + 3 * warp;  // warp-private: full[G0], full[G1], full[G2]
+    Real *g0 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g0());
+    Real *g1 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g1());
+    Real *g2 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g2());
+    Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab));
+    double *acc_s = reinterpret_cast<double *>(smem_raw + TmaSmem<Real>::off_acc(n_lab)) + tid;
+    Real *g0w = g0 + 32 * warp, *g1w = g1 + 32 * warp, *g2w = g2 + 32 * warp;  // this warp's 32-column slice
 
-    if (tid == 0) {
+    if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == 0) {
-        if (prm.T > 0) issue_step_loads(prm, 0, s0, n_ch, stage, &bars[0], lane);
-        if (prm.T > 1) issue_step_loads(prm, 1, s0, n_ch, stage + stage_elems, &bars[1], lane);
+    __syncwarp();
+    if (prm.T > 0) {
+        issue_group<Real, 0>(prm, 0, s_warp, TMA_CH_G0, g0w, &bars[0], lane);
+        issue_group<Real, 1>(prm, 0, s_warp, TMA_CH_G1, g1w, &bars[1], lane);
+        if (n_lab) issue_group<Real, 2>(prm, 0, s_warp, 12 * n_lab, g2w, &bars[2], lane);
     }
 
-    Real *q = noise + tid, *r = noise + 12 * nt + tid, *rinv = noise + 22 * nt + tid;
+    Real *q = noise + tid, *r = noise + 12 * nt + tid;
 #pragma unroll
     for (int c = 0; c < NX; ++c) q[c * nt] = prm.q_kind == OPTI_KF_MAT_DIAG ? prm.Q[c] : prm.Q[c * N + ic];
 #pragma unroll
-    for (int c = 0; c < NZ; ++c) {
-        const Real rv = prm.r_kind == OPTI_KF_MAT_DIAG ? prm.R[c] : prm.R[c * N + ic];
-        r[c * nt] = rv;
-        rinv[c * nt] = Real(1) / rv;
-    }
+    for (int c = 0; c < NZ; ++c) r[c * nt] = prm.r_kind == OPTI_KF_MAT_DIAG ? prm.R[c] : prm.R[c * N + ic];
     Real x[NX], P[NP];
 #pragma unroll
     for (int c = 0; c < NX; ++c) x[c] = prm.x0[c * prm.x0_ld + ic * prm.x0_inc];
@@ -143,9 +237,9 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
 
     uint32_t status = 0;
     Real ptrace = Real(0), kgain = Real(0), ymax = Real(0);
-    constexpr int kAccRegs = (kSummary && !kAccSmem) ? 25 : 1;
+    constexpr int kAccRegs = (kSummary && !kAccSmem) ? TMA_ACC_ROWS : 1;
     double acc_r[kAccRegs];
-    auto acc_add = [&](int idx, double v) {  // running sums: 0-11 truth, 12-23 nominal, 24 NIS
+    auto acc_add = [&](int idx, double v) {
         if constexpr (kAccSmem) acc_s[idx * nt] += v;
         else if constexpr (kSummary) acc_r[idx] += v;
     };
@@ -156,21 +250,29 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     };
     if constexpr (kSummary) {
 #pragma unroll
-        for (int c = 0; c < 25; ++c) {
+        for (int c = 0; c < TMA_ACC_ROWS; ++c) {
             if constexpr (kAccSmem) acc_s[c * nt] = 0.0; else acc_r[c] = 0.0;
         }
     }
-    const bool want_gain = prm.k_gain_steps != nullptr || prm.summary != nullptr;
+
+    // rotation of the prior attitude for step 0; inside the loop it is produced one step ahead
+    Real Rm[9];
+    rot_zyx(x[0], x[1], x[2], Rm);
+    bool any_trunc = may_truncate(Rm);
 
     for (long long t = 0; t < prm.T; ++t) {
-        const int st = (int)(t & 1);
-        mbar_wait(&bars[st], (uint32_t)((t >> 1) & 1));
-        const Real *in = stage + st * stage_elems + tid;
+        const uint32_t par = (uint32_t)(t & 1);
+        const bool more = t + 1 < prm.T;
+        const bool last = !more;
 
-        Real pf[12], ff[12], Rm[9];
+        // ---- G0: feet and forces -> mean model --------------------------------------------------------------
+        mbar_wait(&bars[0], par);
+        Real pf[12], ff[12];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) { pf[c] = in[c * nt]; ff[c] = in[(12 + c) * nt]; }
-        propagate_mean(prm, x, pf, ff, Rm);
+        for (int c = 0; c < 12; ++c) { pf[c] = g0[c * nt + tid]; ff[c] = g0[(12 + c) * nt + tid]; }
+        __syncwarp();
+        if (more) issue_group<Real, 0>(prm, t + 1, s_warp, TMA_CH_G0, g0w, &bars[0], lane);
+        propagate_mean_with_R(prm, x, pf, ff, Rm, any_trunc);
         if (active) {
             if (prm.x_model_steps) {
 #pragma unroll
@@ -180,34 +282,50 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
 #pragma unroll
                 for (int c = 0; c < 12; ++c) st_stream(prm.p_world_steps + (t * 12 + c) * N + i, pf[c]);
             }
-            if (prm.z_steps) {
-#pragma unroll
-                for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, in[(24 + c) * nt]);
-            }
         }
 
         cov_predict_sym(P, Rm, prm.dt, q, nt);
 
-        Real nis = Real(0);
-        fold_measurement<0>(P, x, in[24 * nt], r[0 * nt], nis, status);
-        fold_measurement<1>(P, x, in[25 * nt], r[1 * nt], nis, status);
-        fold_measurement<2>(P, x, in[26 * nt], r[2 * nt], nis, status);
-        fold_measurement<3>(P, x, in[27 * nt], r[3 * nt], nis, status);
-        fold_measurement<4>(P, x, in[28 * nt], r[4 * nt], nis, status);
-        fold_measurement<5>(P, x, in[29 * nt], r[5 * nt], nis, status);
-        fold_measurement<6>(P, x, in[30 * nt], r[6 * nt], nis, status);
-        fold_measurement<7>(P, x, in[31 * nt], r[7 * nt], nis, status);
-        fold_measurement<8>(P, x, in[32 * nt], r[8 * nt], nis, status);
-        fold_measurement<9>(P, x, in[33 * nt], r[9 * nt], nis, status);
+        // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
+        mbar_wait(&bars[1], par);
+        const Real *z = g1 + tid;
+        if (active && prm.z_steps) {
+#pragma unroll
+            for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, z[c * nt]);
+        }
+        Real nis = Real(0), inv, inv_n;
+        {
+            const Real s = P[tri(0, 0)] + r[0];
+            if (!(s > Real(0)) || !(s < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
+            inv = Real(1) / s;
+        }
+        auto nothing = [] {};
+        fold_pipelined<0>(P, x, z[0 * nt], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<1>(P, x, z[1 * nt], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<2>(P, x, z[2 * nt], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<3>(P, x, z[3 * nt], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<4>(P, x, z[4 * nt], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<5>(P, x, z[5 * nt], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<6>(P, x, z[6 * nt], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<7>(P, x, z[7 * nt], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<8>(P, x, z[8 * nt], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        const Real z9 = z[9 * nt], r9 = r[9 * nt];
+        __syncwarp();  // every lane has read its last measurement of this step: refill G1 for step t + 1
+        if (more) issue_group<Real, 1>(prm, t + 1, s_warp, TMA_CH_G1, g1w, &bars[1], lane);
+        fold_pipelined<9>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
+            // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
+            rot_zyx(x[0], x[1], x[2], Rm);
+            any_trunc = may_truncate(Rm);
+        });
 
         ymax = fmax(ymax, nis);
         ptrace = Real(0);
 #pragma unroll
         for (int c = 0; c < NX; ++c) ptrace += P[tri(c, c)];
-        if (want_gain) {
-            kgain = Real(0);
+        if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
+            kgain = Real(0);  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
 #pragma unroll
-            for (int j = 0; j < NZ; ++j) kgain += P[tri(j, sel(j))] * rinv[j * nt];
+            for (int j = 0; j < NZ; ++j) kgain += P[tri(j, sel(j))] / r[j * nt];
         }
         bool fin = true;
 #pragma unroll
@@ -230,27 +348,32 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
                     for (int b = 0; b < NX; ++b) dst[(long long)(a * NX + b) * N] = P[tri(a, b)];
             }
         }
+
+        // ---- G2: label streams -> running error sums -------------------------------------------------------------
         if constexpr (kSummary) {
             acc_add(24, (double)nis);
-            if (prm.truth) {
+            if (n_lab) {
+                mbar_wait(&bars[2], par);
+                const Real *lab = g2 + tid;
+                if (prm.truth) {
 #pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    const double e = (double)x[c] - (double)in[(34 + c) * nt];
-                    acc_add(c, e * e);
+                    for (int c = 0; c < NX; ++c) {
+                        const double e = (double)x[c] - (double)lab[c * nt];
+                        acc_add(c, e * e);
+                    }
                 }
-            }
-            if (prm.nominal) {
-                const int base = prm.truth ? 46 : 34;
+                if (prm.nominal) {
+                    const int base = prm.truth ? 12 : 0;
 #pragma unroll
-                for (int c = 0; c < NX; ++c) {
-                    const double e = (double)x[c] - (double)in[(base + c) * nt];
-                    acc_add(12 + c, e * e);
+                    for (int c = 0; c < NX; ++c) {
+                        const double e = (double)x[c] - (double)lab[(base + c) * nt];
+                        acc_add(12 + c, e * e);
+                    }
                 }
+                __syncwarp();
+                if (more) issue_group<Real, 2>(prm, t + 1, s_warp, 12 * n_lab, g2w, &bars[2], lane);
             }
         }
-
-        __syncthreads();  // every thread is done with stage `st`: refill it with step t + 2
-        if (warp == 0 && t + TMA_STAGES < prm.T) issue_step_loads(prm, t + TMA_STAGES, s0, n_ch, stage + st * stage_elems, &bars[st], lane);
     }
 
     if (!active) return;
@@ -279,7 +402,7 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
         sm[50LL * N] = kgain;
         sm[51LL * N] = (Real)sqrt((double)ymax);
     }
-    if (prm.status) prm.status[i] = status | (prm.stream_status ? prm.stream_status[(s0 + tid) % S] : 0u);
+    if (prm.status) prm.status[i] = status | (prm.stream_status ? prm.stream_status[(s_warp + lane) % S] : 0u);
 }
 
 }  // namespace okf
