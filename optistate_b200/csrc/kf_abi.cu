@@ -93,23 +93,61 @@ size_t seq_workspace_bytes(const OptiKfDesc *d) {
     return z_bytes + (((size_t)d->n_streams * sizeof(uint32_t) + 255) & ~(size_t)255);
 }
 
-// The streamed kernel needs 128 consecutive trajectories to read 128 consecutive, 16-byte aligned streams.
+// The streamed kernel needs every warp (32 consecutive trajectories) to read one aligned tile of 32 consecutive
+// streams, 16-byte aligned arrays and row counts that fit the 32-bit tensor-map coordinates.
 bool tma_layout_ok(const OptiKfDesc *d) {
     if (d->stream_index != nullptr || d->n_steps == 0) return false;
-    if (d->n_streams % okf::TMA_THREADS != 0 || d->stream_offset % okf::TMA_THREADS != 0) return false;
+    if (d->n_streams % 32 != 0 || d->stream_offset % 32 != 0) return false;
+    if (d->n_steps * 12 >= (1LL << 31)) return false;
     if (!aligned16(d->p) || !aligned16(d->f)) return false;
     if (d->summary && ((d->truth && !aligned16(d->truth)) || (d->nominal && !aligned16(d->nominal)))) return false;
     return true;
 }
 
+// cuTensorMapEncodeTiled, fetched from the driver through the runtime (no link-time dependency on libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static const EncodeTiledFn fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return (EncodeTiledFn)sym;
+    }();
+    return fn;
+}
+
+// [T*C][S] matrix of one per-step input array, fetched in [C][32] boxes (one warp's tile of one step)
+template <typename Real>
+bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || !base) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)(T * C)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)S * sizeof(Real)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)C};
+    const cuuint32_t estride[2] = {1u, 1u};
+    return enc(m, sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride,
+               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns OPTI_KF_OK, an error, or +1 when the tensor maps could not be built (caller falls back to the direct kernel)
 template <typename Real, bool kSummary>
 int launch_seq_tma(const okf::Params<Real> &p, cudaStream_t stream) {
     const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
+    okf::TmaMaps maps;
+    std::memset(&maps, 0, sizeof maps);
+    bool ok = make_map(&maps.p, p.p, p.T, 12, p.S) && make_map(&maps.f, p.f, p.T, 12, p.S) && make_map(&maps.z, p.z_in, p.T, 10, p.S);
+    if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S);
+    if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S);
+    if (!ok) return 1;
     const size_t smem = okf::TmaSmem<Real>::total(n_lab, kSummary && sizeof(Real) == 8);
     auto kern = okf::kf_seq_tma_kernel<Real, kSummary>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     const unsigned blocks = (unsigned)((p.N + okf::TMA_THREADS - 1) / okf::TMA_THREADS);
-    kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p);
+    kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p, maps);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return OPTI_KF_OK;
 }
@@ -141,8 +179,9 @@ int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
         }
         if (streamed) {
             const int rc = d->summary ? launch_seq_tma<Real, true>(p, stream) : launch_seq_tma<Real, false>(p, stream);
-            if (rc != OPTI_KF_OK) return rc;
-            return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+            if (rc < 0) return rc;
+            if (rc == OPTI_KF_OK) return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+            // tensor maps unavailable: the direct-load kernel below consumes the same (pre-formed) z
         }
         constexpr int kThreads = 128;
         const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);

@@ -1,11 +1,12 @@
 // Throughput kernel, streamed variant: same arithmetic as kf_seq.cuh (one thread per trajectory, packed symmetric
 // P and x in registers, sequential scalar updates) with the per-step inputs delivered by the TMA engine.
 //
-//   * 32 consecutive trajectories (one warp) read 32 consecutive base streams, so every input channel of one
-//     step is one contiguous 32-element run of the [T][C][S] layout.  Each warp runs its OWN input pipeline:
-//     its lanes issue one cp.async.bulk (global -> shared, completion on a warp-private mbarrier with
-//     complete_tx) per channel.  No per-thread address arithmetic, no LDG in the recursion, no registers tied
-//     up by loads in flight, and no block-wide barrier: warps never wait for each other.
+//   * 32 consecutive trajectories (one warp) read 32 consecutive base streams, so the inputs of one step are
+//     [C] x 32 tiles of the [T*C][S] arrays.  Each warp runs its OWN input pipeline: one elected lane issues a
+//     2-D tensor-map copy (cp.async.bulk.tensor, SASS UTMALDG) per array - p, f, z, label streams - that lands the
+//     tile in the warp's slice of shared memory and completes on a warp-private mbarrier (complete_tx).  No
+//     per-thread address arithmetic, no LDG in the recursion, no registers tied up by loads in flight, and no
+//     block-wide barrier: warps never wait for each other.
 //   * Three channel groups, each single-buffered and refilled for step t+1 the moment the warp has consumed
 //     step t's copy, so the copy has most of a filter step (several microseconds) to land:
 //         G0 = p[12] f[12]      read at the top of the step (mean model)        -> refilled right away
@@ -19,6 +20,8 @@
 //   * z comes from the measurement pre-pass (optistate_kf_measure): it is state-independent and, with shared
 //     base streams, identical for every Monte-Carlo member of a stream.
 #pragma once
+
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "kf_seq.cuh"
 
@@ -53,39 +56,54 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+// tensor maps of the per-step input arrays, each viewed as a [T*C][S] matrix with a [C][32] box
+struct alignas(64) TmaMaps {
+    CUtensorMap p, f, z, lab0, lab1;
+};
+
+__device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, int col, int row, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <typename Real>
 struct TmaSmem {
-    // byte offsets inside dynamic shared memory; every array is [rows][TMA_THREADS]
-    static __host__ __device__ constexpr size_t rows(int n) { return (size_t)n * TMA_THREADS * sizeof(Real); }
-    static __host__ __device__ constexpr size_t off_g0() { return 128; }  // mbarriers live in the first 128 bytes
-    static __host__ __device__ constexpr size_t off_g1() { return off_g0() + rows(TMA_CH_G0); }
-    static __host__ __device__ constexpr size_t off_g2() { return off_g1() + rows(TMA_CH_G1); }
-    static __host__ __device__ constexpr size_t off_noise(int n_lab) { return off_g2() + rows(12 * n_lab); }
-    static __host__ __device__ constexpr size_t off_acc(int n_lab) { return off_noise(n_lab) + rows(TMA_NOISE_ROWS); }
+    // dynamic shared memory: [mbarriers 128 B][per warp: G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32]] x 4 warps
+    //                        [noise [22][128]][acc [25][128] doubles (FP64 summary only)]
+    static __host__ __device__ constexpr size_t warp_rows(int n_lab) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab; }
+    static __host__ __device__ constexpr size_t warp_bytes(int n_lab) { return warp_rows(n_lab) * 32 * sizeof(Real); }
+    static __host__ __device__ constexpr size_t off_in() { return 128; }
+    static __host__ __device__ constexpr size_t off_noise(int n_lab) { return off_in() + TMA_WARPS * warp_bytes(n_lab); }
+    static __host__ __device__ constexpr size_t off_acc(int n_lab) { return off_noise(n_lab) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
     static __host__ __device__ constexpr size_t total(int n_lab, bool acc_in_smem) {
         return off_acc(n_lab) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * sizeof(double) : 0);
     }
 };
 
-// One warp, one channel group of step t: lane c copies channel c (32 consecutive streams) into the warp's slice.
-//   group 0: p[0..11] f[0..11]   group 1: z[0..9]   group 2: label streams (truth first when both are present)
-template <typename Real, int G>
-__device__ __forceinline__ void issue_group(const Params<Real> &prm, long long t, long long s_warp, int n_ch, Real *dst_warp,
-                                            uint64_t *bar, int lane) {
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_ch * 32 * sizeof(Real)));
-    __syncwarp();
-    if (lane < n_ch) {
-        const Real *arr;
-        int C, c;
-        if (G == 0) {
-            arr = lane < 12 ? prm.p : prm.f; C = 12; c = lane < 12 ? lane : lane - 12;
-        } else if (G == 1) {
-            arr = prm.z_in; C = 10; c = lane;
-        } else {
-            const Real *lab0 = prm.truth ? prm.truth : prm.nominal;
-            arr = lane < 12 ? lab0 : prm.nominal; C = 12; c = lane < 12 ? lane : lane - 12;
-        }
-        bulk_g2s(dst_warp + lane * TMA_THREADS, arr + (t * C + c) * prm.S + s_warp, (uint32_t)(32 * sizeof(Real)), bar);
+// One elected lane per warp: arm the group's mbarrier with the byte count, then issue the tile copies of step t.
+template <typename Real>
+__device__ __forceinline__ void issue_g0(const TmaMaps &m, long long t, int s_warp, Real *g0w, uint64_t *bar, int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(TMA_CH_G0 * 32 * sizeof(Real)));
+        tma_tile_g2s(g0w, &m.p, s_warp, (int)(t * 12), bar);
+        tma_tile_g2s(g0w + 12 * 32, &m.f, s_warp, (int)(t * 12), bar);
+    }
+}
+template <typename Real>
+__device__ __forceinline__ void issue_g1(const TmaMaps &m, long long t, int s_warp, Real *g1w, uint64_t *bar, int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(TMA_CH_G1 * 32 * sizeof(Real)));
+        tma_tile_g2s(g1w, &m.z, s_warp, (int)(t * 10), bar);
+    }
+}
+template <typename Real>
+__device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_warp, int n_lab, Real *g2w, uint64_t *bar, int lane) {
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(12 * n_lab * 32 * sizeof(Real)));
+        tma_tile_g2s(g2w, &m.lab0, s_warp, (int)(t * 12), bar);
+        if (n_lab > 1) tma_tile_g2s(g2w + 12 * 32, &m.lab1, s_warp, (int)(t * 12), bar);
     }
 }
 
@@ -178,7 +196,8 @@ __device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
 }
 
 template <typename Real, bool kSummary>
-__global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_constant__ Params<Real> prm) {
+__global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_constant__ Params<Real> prm,
+                                                                 const __grid_constant__ TmaMaps maps) {
     constexpr bool kAccSmem = kSummary && sizeof(Real) == 8;  // FP64: the 25 running sums do not fit next to P in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int nt = TMA_THREADS;
@@ -188,16 +207,14 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     const long long i = i0 + tid;
     const bool active = i < N;
     const long long ic = active ? i : N - 1;  // clamped index for per-trajectory parameter loads
-    const long long s_warp = (i0 + prm.stream_offset) % S + 32 * warp;
+    const int s_warp = (int)((i0 + 32 * warp + prm.stream_offset) % S);  // first stream of this warp's tile
     const int n_lab = kSummary ? (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0) : 0;
 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + 3 * warp;  // warp-private: full[G0], full[G1], full[G2]
-    Real *g0 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g0());
-    Real *g1 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g1());
-    Real *g2 = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_g2());
+    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in() + warp * TmaSmem<Real>::warp_bytes(n_lab));
+    Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // this warp's [C][32] tiles
     Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab));
     double *acc_s = reinterpret_cast<double *>(smem_raw + TmaSmem<Real>::off_acc(n_lab)) + tid;
-    Real *g0w = g0 + 32 * warp, *g1w = g1 + 32 * warp, *g2w = g2 + 32 * warp;  // this warp's 32-column slice
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -207,9 +224,9 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     }
     __syncwarp();
     if (prm.T > 0) {
-        issue_group<Real, 0>(prm, 0, s_warp, TMA_CH_G0, g0w, &bars[0], lane);
-        issue_group<Real, 1>(prm, 0, s_warp, TMA_CH_G1, g1w, &bars[1], lane);
-        if (n_lab) issue_group<Real, 2>(prm, 0, s_warp, 12 * n_lab, g2w, &bars[2], lane);
+        issue_g0(maps, 0, s_warp, g0w, &bars[0], lane);
+        issue_g1(maps, 0, s_warp, g1w, &bars[1], lane);
+        if (n_lab) issue_g2(maps, 0, s_warp, n_lab, g2w, &bars[2], lane);
     }
 
     Real *q = noise + tid, *r = noise + 12 * nt + tid;
@@ -269,9 +286,9 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
         mbar_wait(&bars[0], par);
         Real pf[12], ff[12];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) { pf[c] = g0[c * nt + tid]; ff[c] = g0[(12 + c) * nt + tid]; }
+        for (int c = 0; c < 12; ++c) { pf[c] = g0w[c * 32 + lane]; ff[c] = g0w[(12 + c) * 32 + lane]; }
         __syncwarp();
-        if (more) issue_group<Real, 0>(prm, t + 1, s_warp, TMA_CH_G0, g0w, &bars[0], lane);
+        if (more) issue_g0(maps, t + 1, s_warp, g0w, &bars[0], lane);
         propagate_mean_with_R(prm, x, pf, ff, Rm, any_trunc);
         if (active) {
             if (prm.x_model_steps) {
@@ -288,10 +305,10 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
         mbar_wait(&bars[1], par);
-        const Real *z = g1 + tid;
+        const Real *z = g1w + lane;
         if (active && prm.z_steps) {
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, z[c * nt]);
+            for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, z[c * 32]);
         }
         Real nis = Real(0), inv, inv_n;
         {
@@ -300,18 +317,18 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
             inv = Real(1) / s;
         }
         auto nothing = [] {};
-        fold_pipelined<0>(P, x, z[0 * nt], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<1>(P, x, z[1 * nt], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<2>(P, x, z[2 * nt], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<3>(P, x, z[3 * nt], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<4>(P, x, z[4 * nt], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<5>(P, x, z[5 * nt], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<6>(P, x, z[6 * nt], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<7>(P, x, z[7 * nt], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<8>(P, x, z[8 * nt], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        const Real z9 = z[9 * nt], r9 = r[9 * nt];
+        fold_pipelined<0>(P, x, z[0 * 32], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<1>(P, x, z[1 * 32], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<2>(P, x, z[2 * 32], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<3>(P, x, z[3 * 32], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<4>(P, x, z[4 * 32], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<5>(P, x, z[5 * 32], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<6>(P, x, z[6 * 32], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<7>(P, x, z[7 * 32], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<8>(P, x, z[8 * 32], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        const Real z9 = z[9 * 32], r9 = r[9 * nt];
         __syncwarp();  // every lane has read its last measurement of this step: refill G1 for step t + 1
-        if (more) issue_group<Real, 1>(prm, t + 1, s_warp, TMA_CH_G1, g1w, &bars[1], lane);
+        if (more) issue_g1(maps, t + 1, s_warp, g1w, &bars[1], lane);
         fold_pipelined<9>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
             // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
             rot_zyx(x[0], x[1], x[2], Rm);
@@ -354,11 +371,11 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
             acc_add(24, (double)nis);
             if (n_lab) {
                 mbar_wait(&bars[2], par);
-                const Real *lab = g2 + tid;
+                const Real *lab = g2w + lane;
                 if (prm.truth) {
 #pragma unroll
                     for (int c = 0; c < NX; ++c) {
-                        const double e = (double)x[c] - (double)lab[c * nt];
+                        const double e = (double)x[c] - (double)lab[c * 32];
                         acc_add(c, e * e);
                     }
                 }
@@ -366,12 +383,12 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
                     const int base = prm.truth ? 12 : 0;
 #pragma unroll
                     for (int c = 0; c < NX; ++c) {
-                        const double e = (double)x[c] - (double)lab[(base + c) * nt];
+                        const double e = (double)x[c] - (double)lab[(base + c) * 32];
                         acc_add(12 + c, e * e);
                     }
                 }
                 __syncwarp();
-                if (more) issue_group<Real, 2>(prm, t + 1, s_warp, 12 * n_lab, g2w, &bars[2], lane);
+                if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], lane);
             }
         }
     }
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
         sm[50LL * N] = kgain;
         sm[51LL * N] = (Real)sqrt((double)ymax);
     }
-    if (prm.status) prm.status[i] = status | (prm.stream_status ? prm.stream_status[(s_warp + lane) % S] : 0u);
+    if (prm.status) prm.status[i] = status | (prm.stream_status ? prm.stream_status[s_warp + lane] : 0u);
 }
 
 }  // namespace okf
