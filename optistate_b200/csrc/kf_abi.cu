@@ -2,6 +2,7 @@
 // the POD descriptor into typed kernel parameters, kernel selection and launch.  No torch types, no allocation,
 // no exceptions; every failure is a negative return code.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "kf_joint.cuh"
@@ -121,12 +122,12 @@ EncodeTiledFn encode_tiled() {
 
 // [T*C][S] matrix of one per-step input array, fetched in [C][32] boxes (one warp's tile of one step)
 template <typename Real>
-bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S) {
+bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S, int box_w) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc || !base) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)(T * C)};
     const cuuint64_t gstride[1] = {(cuuint64_t)S * sizeof(Real)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)C};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)C};
     const cuuint32_t estride[2] = {1u, 1u};
     return enc(m, sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride,
                box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -134,22 +135,52 @@ bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S)
 }
 
 // returns OPTI_KF_OK, an error, or +1 when the tensor maps could not be built (caller falls back to the direct kernel)
+// Real = double | float | okf::F2 (two FP32 trajectories per thread)
 template <typename Real, bool kSummary>
-int launch_seq_tma(const okf::Params<Real> &p, cudaStream_t stream) {
+int launch_seq_tma(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    constexpr int L = okf::Lanes<Real>::n;
     const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
     okf::TmaMaps maps;
     std::memset(&maps, 0, sizeof maps);
-    bool ok = make_map(&maps.p, p.p, p.T, 12, p.S) && make_map(&maps.f, p.f, p.T, 12, p.S) && make_map(&maps.z, p.z_in, p.T, 10, p.S);
-    if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S);
-    if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S);
+    const int bw = 32 * L;
+    bool ok = make_map(&maps.p, p.p, p.T, 12, p.S, bw) && make_map(&maps.f, p.f, p.T, 12, p.S, bw) && make_map(&maps.z, p.z_in, p.T, 10, p.S, bw);
+    if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw);
+    if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw);
     if (!ok) return 1;
     const size_t smem = okf::TmaSmem<Real>::total(n_lab, kSummary && sizeof(Real) == 8);
     auto kern = okf::kf_seq_tma_kernel<Real, kSummary>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
-    const unsigned blocks = (unsigned)((p.N + okf::TMA_THREADS - 1) / okf::TMA_THREADS);
+    const long long per_block = (long long)okf::TMA_THREADS * L;
+    const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
     kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p, maps);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return OPTI_KF_OK;
+}
+
+inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+// FP32 only: two trajectories per thread on the packed FFMA2 path need even counts, 64-stream tiles and 8-byte
+// aligned per-trajectory arrays (every [C][N] row then starts on a float2 boundary).
+bool packed_pair_ok(const OptiKfDesc *d) {
+    if (d->dtype != OPTI_KF_F32 || std::getenv("OPTISTATE_KF_NO_PACKED")) return false;
+    if (d->n_traj % 2 != 0 || d->n_streams % 64 != 0 || d->stream_offset % 64 != 0) return false;
+    const void *ptrs[] = {d->x0, d->P0, d->Q, d->R, d->x_steps, d->x_model_steps, d->p_world_steps, d->z_steps, d->p_trace_steps,
+                          d->k_gain_steps, d->nis_steps, d->P_ckpt, d->x_final, d->P_final, d->summary};
+    for (const void *q : ptrs)
+        if (q && !aligned8(q)) return false;
+    return true;
+}
+
+template <typename Scalar>
+int launch_streamed(const OptiKfDesc *d, const okf::Params<Scalar> &p, cudaStream_t stream);
+template <>
+int launch_streamed<double>(const OptiKfDesc *d, const okf::Params<double> &p, cudaStream_t stream) {
+    return d->summary ? launch_seq_tma<double, true>(p, stream) : launch_seq_tma<double, false>(p, stream);
+}
+template <>
+int launch_streamed<float>(const OptiKfDesc *d, const okf::Params<float> &p, cudaStream_t stream) {
+    if (packed_pair_ok(d)) return d->summary ? launch_seq_tma<okf::F2, true>(p, stream) : launch_seq_tma<okf::F2, false>(p, stream);
+    return d->summary ? launch_seq_tma<float, true>(p, stream) : launch_seq_tma<float, false>(p, stream);
 }
 
 template <typename Real>
@@ -178,7 +209,7 @@ int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
             streamed = false;
         }
         if (streamed) {
-            const int rc = d->summary ? launch_seq_tma<Real, true>(p, stream) : launch_seq_tma<Real, false>(p, stream);
+            const int rc = launch_streamed<Real>(d, p, stream);
             if (rc < 0) return rc;
             if (rc == OPTI_KF_OK) return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
             // tensor maps unavailable: the direct-load kernel below consumes the same (pre-formed) z

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/optistate_kf.h"
+#include "kf_arith.cuh"
 
 namespace okf {
 
@@ -36,12 +37,18 @@ struct Params {
 template <typename Real> __device__ __forceinline__ void sincos_full(Real a, Real &s, Real &c);
 template <> __device__ __forceinline__ void sincos_full<double>(double a, double &s, double &c) { sincos(a, &s, &c); }
 template <> __device__ __forceinline__ void sincos_full<float>(float a, float &s, float &c) { sincosf(a, &s, &c); }
+template <> __device__ __forceinline__ void sincos_full<F2>(F2 a, F2 &s, F2 &c) {
+    sincosf(a.v.x, &s.v.x, &c.v.x);
+    sincosf(a.v.y, &s.v.y, &c.v.y);
+}
 
 // products/sums that must not be contracted into FMAs: the entries of R decide trunc(R^T) below
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ F2 mul_rn(F2 a, F2 b) { return a * b; }  // FMUL2 / FADD2 are never contracted
+__device__ __forceinline__ F2 add_rn(F2 a, F2 b) { return a + b; }
 
 // R = Rz(c) Ry(b) Rx(a), multiplied out in the association np.matmul(Rz, np.matmul(Ry, Rx)) produces
 // (kalman_filter.py:184-193, force_controller.py:227-237).  Row-major R[3*i + j].

@@ -22,9 +22,11 @@ constexpr int NP = 78;
 constexpr int SEQ_NOISE_ROWS = 32;  // shared memory rows per thread: q[12] r[10] 1/r[10]
 
 // P <- F_d P F_d^T + diag(q), F_d = I + dt N, N[a,c] = R^T, N[b,d] = I   (blocks a=0..2 b=3..5 c=6..8 d=9..11)
-template <typename Real>
-__device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9], Real dt, const Real *q, int qs) {
+// Written with explicit fma_ so that double, float and the packed F2 type run the same operation sequence.
+template <typename Real, typename Scalar>
+__device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9], Scalar dt_s, const Real *q, int qs) {
     constexpr int a = 0, b = 3, c = 6, d = 9;
+    const Real dt = Real(dt_s);
     Real A[9];  // A = dt R^T
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -37,17 +39,17 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
         for (int j = 0; j <= i; ++j) {
             Real s = P[tri(a + i, a + j)];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s += A[3 * i + k] * P[tri(c + k, a + j)];
+            for (int k = 0; k < 3; ++k) s = fma_(A[3 * i + k], P[tri(c + k, a + j)], s);
             P[tri(a + i, a + j)] = s;
         }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) P[tri(b + i, a + j)] += dt * P[tri(d + i, a + j)];
+        for (int j = 0; j < 3; ++j) P[tri(b + i, a + j)] = fma_(dt, P[tri(d + i, a + j)], P[tri(b + i, a + j)]);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] += dt * P[tri(d + i, b + j)];
+        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + i, b + j)], P[tri(b + i, b + j)]);
         // P'[c,a] = P[c,a] + P[c,c] A^T ; P'[d,a] = P[d,a] + P[d,c] A^T ; P'[c,b] = P[c,b] + dt P[c,d] ; P'[d,b] = P[d,b] + dt P[d,d]
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -56,8 +58,8 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
             Real s = P[tri(c + i, a + j)], u = P[tri(d + i, a + j)];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                s += P[tri(c + i, c + k)] * A[3 * j + k];
-                u += P[tri(d + i, c + k)] * A[3 * j + k];
+                s = fma_(P[tri(c + i, c + k)], A[3 * j + k], s);
+                u = fma_(P[tri(d + i, c + k)], A[3 * j + k], u);
             }
             P[tri(c + i, a + j)] = s;
             P[tri(d + i, a + j)] = u;
@@ -66,8 +68,8 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            P[tri(c + i, b + j)] += dt * P[tri(d + j, c + i)];
-            P[tri(d + i, b + j)] += dt * P[tri(d + i, d + j)];
+            P[tri(c + i, b + j)] = fma_(dt, P[tri(d + j, c + i)], P[tri(c + i, b + j)]);
+            P[tri(d + i, b + j)] = fma_(dt, P[tri(d + i, d + j)], P[tri(d + i, b + j)]);
         }
         // second factor: + W[a,c] A^T, + W[b,c] A^T, + dt W[b,d], with W[.,c] = P'[c,.]^T and W[b,d] = P'[d,b]^T
 #pragma unroll
@@ -76,7 +78,7 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
         for (int j = 0; j <= i; ++j) {
             Real s = P[tri(a + i, a + j)];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s += P[tri(c + k, a + i)] * A[3 * j + k];
+            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, a + i)], A[3 * j + k], s);
             P[tri(a + i, a + j)] = s;
         }
 #pragma unroll
@@ -85,13 +87,13 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
         for (int j = 0; j < 3; ++j) {
             Real s = P[tri(b + i, a + j)];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s += P[tri(c + k, b + i)] * A[3 * j + k];
+            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, b + i)], A[3 * j + k], s);
             P[tri(b + i, a + j)] = s;
         }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] += dt * P[tri(d + j, b + i)];
+        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + j, b + i)], P[tri(b + i, b + j)]);
 #pragma unroll
     for (int i = 0; i < NX; ++i) P[tri(i, i)] += q[i * qs];
 }

@@ -17,6 +17,8 @@
 //   * Latency of the two long dependent chains is hidden behind the independent rank-1 FMAs: the reciprocal of
 //     the NEXT pivot is started as soon as that pivot's entry has been updated, and the sin/cos of the NEXT
 //     step's attitude are started as soon as the last state update is done.
+//   * Instantiated for double, float and F2 (kf_arith.cuh): F2 packs TWO FP32 trajectories into one thread and runs
+//     the recursion on FFMA2 / FADD2 / FMUL2, halving the issue slots per trajectory-step; its tiles are [C] x 64.
 //   * z comes from the measurement pre-pass (optistate_kf_measure): it is state-independent and, with shared
 //     base streams, identical for every Monte-Carlo member of a stream.
 #pragma once
@@ -71,14 +73,14 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, 
 template <typename Real>
 struct TmaSmem {
     // dynamic shared memory: [mbarriers 128 B][per warp: G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32]] x 4 warps
-    //                        [noise [22][128]][acc [25][128] doubles (FP64 summary only)]
+    //                        [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
     static __host__ __device__ constexpr size_t warp_rows(int n_lab) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab; }
     static __host__ __device__ constexpr size_t warp_bytes(int n_lab) { return warp_rows(n_lab) * 32 * sizeof(Real); }
     static __host__ __device__ constexpr size_t off_in() { return 128; }
     static __host__ __device__ constexpr size_t off_noise(int n_lab) { return off_in() + TMA_WARPS * warp_bytes(n_lab); }
     static __host__ __device__ constexpr size_t off_acc(int n_lab) { return off_noise(n_lab) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
     static __host__ __device__ constexpr size_t total(int n_lab, bool acc_in_smem) {
-        return off_acc(n_lab) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * sizeof(double) : 0);
+        return off_acc(n_lab) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * 8 : 0);
     }
 };
 
@@ -110,24 +112,24 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
 // Measurement J folded in with the reciprocal of its pivot already available (`inv` = 1 / (P_kk + r_J)).  The entry
 // that becomes the NEXT pivot is updated first and its reciprocal started at once, so that chain (MUFU + Newton
 // steps) runs underneath the 65 remaining independent FMAs of this rank-1 update.  `mid` runs after the state update.
-template <int J, typename Real, typename Mid>
+template <int J, typename Real, int L, typename Mid>
 __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Real zj, Real rj, Real r_next, Real inv, Real &inv_next,
-                                               Real &nis, uint32_t &status, Mid mid) {
+                                               Real &nis, uint32_t (&status)[L], Mid mid) {
     constexpr int k = sel(J);
     constexpr int kn = (J + 1 < NZ) ? sel(J + 1) : -1;
     if constexpr (kn >= 0) {
         const Real wn = P[tri(kn, k)] * inv;
-        const Real pnn = P[tri(kn, kn)] - wn * P[tri(kn, k)];
+        const Real pnn = fnma_(wn, P[tri(kn, k)], P[tri(kn, kn)]);
         P[tri(kn, kn)] = pnn;
         const Real s = pnn + r_next;
-        if (!(s > Real(0)) || !(s < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
-        inv_next = Real(1) / s;
+        note_bad_pivot(s, status, OPTI_KF_ST_NOT_PD);
+        inv_next = rcp_(s);
     }
     const Real y = zj - x[k];
     const Real g = inv * y;
-    nis += y * g;
+    nis = fma_(y, g, nis);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] += P[tri(i, k)] * g;
+    for (int i = 0; i < NX; ++i) x[i] = fma_(P[tri(i, k)], g, x[i]);
     mid();
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
@@ -136,7 +138,7 @@ __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Rea
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
             if (j == k || (i == kn && j == kn)) continue;
-            P[tri(i, j)] -= w * P[tri(j, k)];
+            P[tri(i, j)] = fnma_(w, P[tri(j, k)], P[tri(i, j)]);
         }
     }
     const Real cfac = rj * inv;
@@ -144,77 +146,91 @@ __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Rea
     for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
 }
 
-// Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
+// cheap test whether trunc(R^T) can have a non-zero entry in any lane (then the exact decision is taken per lane)
 template <typename Real>
-__device__ __forceinline__ void propagate_mean_with_R(const Params<Real> &prm, Real (&x)[NX], Real (&p)[12], const Real (&f)[12],
+__device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
+    using S = typename Lanes<Real>::scalar;
+    S m = S(0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m = max_(m, absmax_lanes(R[k]));
+    return m >= (sizeof(S) == 8 ? S(1) : S(1.0f - 9.5367431640625e-7f));
+}
+
+// Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
+template <typename Real, typename Scalar>
+__device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm, Real (&x)[NX], Real (&p)[12], const Real (&f)[12],
                                                       const Real (&R)[9], bool any_trunc) {
+    constexpr int L = Lanes<Real>::n;
     Real tau[3] = {Real(0), Real(0), Real(0)}, fs[3] = {Real(0), Real(0), Real(0)};
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const Real a = p[3 * l], b = p[3 * l + 1], c = p[3 * l + 2];
-        const Real pw0 = R[0] * a + R[1] * b + R[2] * c;
-        const Real pw1 = R[3] * a + R[4] * b + R[5] * c;
-        const Real pw2 = R[6] * a + R[7] * b + R[8] * c;
+        const Real pw0 = fma_(R[2], c, fma_(R[1], b, R[0] * a));
+        const Real pw1 = fma_(R[5], c, fma_(R[4], b, R[3] * a));
+        const Real pw2 = fma_(R[8], c, fma_(R[7], b, R[6] * a));
         p[3 * l] = pw0; p[3 * l + 1] = pw1; p[3 * l + 2] = pw2;
         const Real f0 = f[3 * l], f1 = f[3 * l + 1], f2 = f[3 * l + 2];
-        tau[0] += pw1 * f2 - pw2 * f1;
-        tau[1] += pw2 * f0 - pw0 * f2;
-        tau[2] += pw0 * f1 - pw1 * f0;
+        tau[0] += fnma_(pw2, f1, pw1 * f2);
+        tau[1] += fnma_(pw0, f2, pw2 * f0);
+        tau[2] += fnma_(pw1, f0, pw0 * f1);
         fs[0] += f0; fs[1] += f1; fs[2] += f2;
     }
     Real u[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) u[k] = (R[k] * tau[0] + R[3 + k] * tau[1] + R[6 + k] * tau[2]) * prm.inv_inertia[k];
+    for (int k = 0; k < 3; ++k) u[k] = fma_(R[6 + k], tau[2], fma_(R[3 + k], tau[1], R[k] * tau[0])) * Real(prm.inv_inertia[k]);
     Real dth[3] = {Real(0), Real(0), Real(0)};
-    if (any_trunc) {  // rare: an entry of R is exactly +-1 (axis-aligned attitude); see trunc_rt
-        Real Tm[9];
-        bool any;
-        trunc_rt(R, x, Tm, any);
+    if (any_trunc) {  // rare: an entry of R is exactly +-1 (axis-aligned attitude); exact per-lane decision in trunc_rt
 #pragma unroll
-        for (int i = 0; i < 3; ++i) dth[i] = prm.dt * (Tm[3 * i] * x[6] + Tm[3 * i + 1] * x[7] + Tm[3 * i + 2] * x[8]);
+        for (int ln = 0; ln < L; ++ln) {
+            Scalar Rs[9], Ts[9], ang[3];
+            bool any;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rs[k] = lane_get(R[k], ln);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ang[k] = lane_get(x[k], ln);
+            trunc_rt(Rs, ang, Ts, any);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                lane_set(dth[i], ln, prm.dt * (Ts[3 * i] * lane_get(x[6], ln) + Ts[3 * i + 1] * lane_get(x[7], ln) + Ts[3 * i + 2] * lane_get(x[8], ln)));
+        }
     }
+    const Real dt = Real(prm.dt);
     Real xn[NX];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         xn[i] = x[i] + dth[i];
-        xn[3 + i] = x[3 + i] + prm.dt * x[9 + i];
-        xn[6 + i] = x[6 + i] + prm.dt * (R[3 * i] * u[0] + R[3 * i + 1] * u[1] + R[3 * i + 2] * u[2]);
-        xn[9 + i] = x[9 + i] + prm.dt_over_m * fs[i];
+        xn[3 + i] = fma_(dt, x[9 + i], x[3 + i]);
+        xn[6 + i] = fma_(dt, fma_(R[3 * i + 2], u[2], fma_(R[3 * i + 1], u[1], R[3 * i] * u[0])), x[6 + i]);
+        xn[9 + i] = fma_(Real(prm.dt_over_m), fs[i], x[9 + i]);
     }
-    xn[11] += prm.dt_g;
+    xn[11] += Real(prm.dt_g);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
 }
 
-// cheap test whether trunc(R^T) can have a non-zero entry (then the exact decision is taken in trunc_rt)
-template <typename Real>
-__device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
-    Real m = Real(0);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) m = fmax(m, fabs(R[k]));
-    return m >= (sizeof(Real) == 8 ? Real(1) : Real(1.0f - 9.5367431640625e-7f));
-}
-
 template <typename Real, bool kSummary>
-__global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_constant__ Params<Real> prm,
+__global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
-    constexpr bool kAccSmem = kSummary && sizeof(Real) == 8;  // FP64: the 25 running sums do not fit next to P in registers
+    using Scalar = typename Lanes<Real>::scalar;
+    using AccT = typename Acc<Real>::type;
+    constexpr int L = Lanes<Real>::n;                     // trajectories per thread
+    constexpr bool kAccSmem = kSummary && sizeof(Real) == 8;  // double / F2: the 25 running sums do not fit next to P in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int nt = TMA_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = prm.N, S = prm.S;
-    const long long i0 = (long long)blockIdx.x * nt;
-    const long long i = i0 + tid;
-    const bool active = i < N;
-    const long long ic = active ? i : N - 1;  // clamped index for per-trajectory parameter loads
-    const int s_warp = (int)((i0 + 32 * warp + prm.stream_offset) % S);  // first stream of this warp's tile
+    const long long i0 = (long long)blockIdx.x * nt * L;  // first trajectory of the block
+    const long long i = i0 + (long long)tid * L;           // first trajectory of this thread
+    const bool active = i < N;                             // N % L == 0 is guaranteed by the host
+    const long long ic = active ? i : N - L;               // clamped index for per-trajectory parameter loads
+    const int s_warp = (int)((i0 + 32 * L * warp + prm.stream_offset) % S);  // first stream of this warp's tile
     const int n_lab = kSummary ? (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0) : 0;
 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + 3 * warp;  // warp-private: full[G0], full[G1], full[G2]
     Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in() + warp * TmaSmem<Real>::warp_bytes(n_lab));
-    Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // this warp's [C][32] tiles
+    Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // this warp's [C][32] tiles (of Real)
     Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab));
-    double *acc_s = reinterpret_cast<double *>(smem_raw + TmaSmem<Real>::off_acc(n_lab)) + tid;
+    AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + TmaSmem<Real>::off_acc(n_lab)) + tid;
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -231,12 +247,12 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
 
     Real *q = noise + tid, *r = noise + 12 * nt + tid;
 #pragma unroll
-    for (int c = 0; c < NX; ++c) q[c * nt] = prm.q_kind == OPTI_KF_MAT_DIAG ? prm.Q[c] : prm.Q[c * N + ic];
+    for (int c = 0; c < NX; ++c) q[c * nt] = prm.q_kind == OPTI_KF_MAT_DIAG ? Real(prm.Q[c]) : ld_traj(prm.Q, c * N + ic, Real());
 #pragma unroll
-    for (int c = 0; c < NZ; ++c) r[c * nt] = prm.r_kind == OPTI_KF_MAT_DIAG ? prm.R[c] : prm.R[c * N + ic];
+    for (int c = 0; c < NZ; ++c) r[c * nt] = prm.r_kind == OPTI_KF_MAT_DIAG ? Real(prm.R[c]) : ld_traj(prm.R, c * N + ic, Real());
     Real x[NX], P[NP];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) x[c] = prm.x0[c * prm.x0_ld + ic * prm.x0_inc];
+    for (int c = 0; c < NX; ++c) x[c] = prm.x0_inc ? ld_traj(prm.x0, c * prm.x0_ld + ic, Real()) : Real(prm.x0[c]);
 #pragma unroll
     for (int a = 0; a < NX; ++a)
 #pragma unroll
@@ -244,31 +260,33 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
             Real v;
             switch (prm.p0_kind) {
                 case OPTI_KF_MAT_NONE: v = (a == b) ? q[a * nt] : Real(0); break;
-                case OPTI_KF_MAT_DIAG: v = (a == b) ? prm.P0[a] : Real(0); break;
-                case OPTI_KF_MAT_DIAG_PER: v = (a == b) ? prm.P0[a * N + ic] : Real(0); break;
-                case OPTI_KF_MAT_DENSE: v = prm.P0[a * NX + b]; break;
-                default: v = prm.P0[(long long)(a * NX + b) * N + ic]; break;
+                case OPTI_KF_MAT_DIAG: v = (a == b) ? Real(prm.P0[a]) : Real(0); break;
+                case OPTI_KF_MAT_DIAG_PER: v = (a == b) ? ld_traj(prm.P0, a * N + ic, Real()) : Real(0); break;
+                case OPTI_KF_MAT_DENSE: v = Real(prm.P0[a * NX + b]); break;
+                default: v = ld_traj(prm.P0, (long long)(a * NX + b) * N + ic, Real()); break;
             }
             P[tri(a, b)] = v;
         }
 
-    uint32_t status = 0;
+    uint32_t status[L];
+#pragma unroll
+    for (int ln = 0; ln < L; ++ln) status[ln] = 0;
     Real ptrace = Real(0), kgain = Real(0), ymax = Real(0);
     constexpr int kAccRegs = (kSummary && !kAccSmem) ? TMA_ACC_ROWS : 1;
-    double acc_r[kAccRegs];
-    auto acc_add = [&](int idx, double v) {
-        if constexpr (kAccSmem) acc_s[idx * nt] += v;
-        else if constexpr (kSummary) acc_r[idx] += v;
+    AccT acc_r[kAccRegs];
+    auto acc_add = [&](int idx, AccT v) {  // running sums: 0-11 truth, 12-23 nominal, 24 NIS
+        if constexpr (kAccSmem) acc_s[idx * nt] = acc_s[idx * nt] + v;
+        else if constexpr (kSummary) acc_r[idx] = acc_r[idx] + v;
     };
-    auto acc_get = [&](int idx) -> double {
+    auto acc_get = [&](int idx) -> AccT {
         if constexpr (kAccSmem) return acc_s[idx * nt];
         else if constexpr (kSummary) return acc_r[idx];
-        else return 0.0;
+        else return acc_zero(AccT());
     };
     if constexpr (kSummary) {
 #pragma unroll
         for (int c = 0; c < TMA_ACC_ROWS; ++c) {
-            if constexpr (kAccSmem) acc_s[c * nt] = 0.0; else acc_r[c] = 0.0;
+            if constexpr (kAccSmem) acc_s[c * nt] = acc_zero(AccT()); else acc_r[c] = acc_zero(AccT());
         }
     }
 
@@ -293,11 +311,11 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
         if (active) {
             if (prm.x_model_steps) {
 #pragma unroll
-                for (int c = 0; c < NX; ++c) st_stream(prm.x_model_steps + (t * NX + c) * N + i, x[c]);
+                for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
             }
             if (prm.p_world_steps) {
 #pragma unroll
-                for (int c = 0; c < 12; ++c) st_stream(prm.p_world_steps + (t * 12 + c) * N + i, pf[c]);
+                for (int c = 0; c < 12; ++c) st_traj(prm.p_world_steps, (t * 12 + c) * N + i, pf[c]);
             }
         }
 
@@ -308,13 +326,13 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
         const Real *z = g1w + lane;
         if (active && prm.z_steps) {
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, z[c * 32]);
+            for (int c = 0; c < NZ; ++c) st_traj(prm.z_steps, (t * NZ + c) * N + i, z[c * 32]);
         }
         Real nis = Real(0), inv, inv_n;
         {
             const Real s = P[tri(0, 0)] + r[0];
-            if (!(s > Real(0)) || !(s < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
-            inv = Real(1) / s;
+            note_bad_pivot(s, status, OPTI_KF_ST_NOT_PD);
+            inv = rcp_(s);
         }
         auto nothing = [] {};
         fold_pipelined<0>(P, x, z[0 * 32], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
@@ -335,57 +353,49 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
             any_trunc = may_truncate(Rm);
         });
 
-        ymax = fmax(ymax, nis);
+        ymax = max_(ymax, nis);
         ptrace = Real(0);
 #pragma unroll
         for (int c = 0; c < NX; ++c) ptrace += P[tri(c, c)];
         if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
             kgain = Real(0);  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
 #pragma unroll
-            for (int j = 0; j < NZ; ++j) kgain += P[tri(j, sel(j))] / r[j * nt];
+            for (int j = 0; j < NZ; ++j) kgain += div_(P[tri(j, sel(j))], r[j * nt]);
         }
-        bool fin = true;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) fin &= isfinite(x[c]);
-        if (!fin) status |= OPTI_KF_ST_NONFINITE;
+        for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
 
         if (active) {
             if (prm.x_steps) {
 #pragma unroll
-                for (int c = 0; c < NX; ++c) st_stream(prm.x_steps + (t * NX + c) * N + i, x[c]);
+                for (int c = 0; c < NX; ++c) st_traj(prm.x_steps, (t * NX + c) * N + i, x[c]);
             }
-            if (prm.p_trace_steps) st_stream(prm.p_trace_steps + t * N + i, ptrace);
-            if (prm.k_gain_steps) st_stream(prm.k_gain_steps + t * N + i, kgain);
-            if (prm.nis_steps) st_stream(prm.nis_steps + t * N + i, nis);
+            if (prm.p_trace_steps) st_traj(prm.p_trace_steps, t * N + i, ptrace);
+            if (prm.k_gain_steps) st_traj(prm.k_gain_steps, t * N + i, kgain);
+            if (prm.nis_steps) st_traj(prm.nis_steps, t * N + i, nis);
             if (prm.P_ckpt && prm.ckpt_every > 0 && (t + 1) % prm.ckpt_every == 0) {
-                Real *dst = prm.P_ckpt + ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
+                const long long base = ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
 #pragma unroll
                 for (int a = 0; a < NX; ++a)
 #pragma unroll
-                    for (int b = 0; b < NX; ++b) dst[(long long)(a * NX + b) * N] = P[tri(a, b)];
+                    for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
             }
         }
 
         // ---- G2: label streams -> running error sums -------------------------------------------------------------
         if constexpr (kSummary) {
-            acc_add(24, (double)nis);
+            acc_add(24, to_acc(nis));
             if (n_lab) {
                 mbar_wait(&bars[2], par);
                 const Real *lab = g2w + lane;
                 if (prm.truth) {
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) {
-                        const double e = (double)x[c] - (double)lab[c * 32];
-                        acc_add(c, e * e);
-                    }
+                    for (int c = 0; c < NX; ++c) acc_add(c, err_sq(x[c], lab[c * 32]));
                 }
                 if (prm.nominal) {
                     const int base = prm.truth ? 12 : 0;
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) {
-                        const double e = (double)x[c] - (double)lab[(base + c) * 32];
-                        acc_add(12 + c, e * e);
-                    }
+                    for (int c = 0; c < NX; ++c) acc_add(12 + c, err_sq(x[c], lab[(base + c) * 32]));
                 }
                 __syncwarp();
                 if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], lane);
@@ -396,30 +406,33 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     if (!active) return;
     if (prm.x_final) {
 #pragma unroll
-        for (int c = 0; c < NX; ++c) prm.x_final[c * N + i] = x[c];
+        for (int c = 0; c < NX; ++c) st_traj(prm.x_final, c * N + i, x[c]);
     }
     if (prm.P_final) {
 #pragma unroll
         for (int a = 0; a < NX; ++a)
 #pragma unroll
-            for (int b = 0; b < NX; ++b) prm.P_final[(long long)(a * NX + b) * N + i] = P[tri(a, b)];
+            for (int b = 0; b < NX; ++b) st_traj(prm.P_final, (long long)(a * NX + b) * N + i, P[tri(a, b)]);
     }
     if (kSummary && prm.summary) {
-        Real *sm = prm.summary + i;
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            sm[(long long)c * N] = x[c];
-            sm[(long long)(12 + c) * N] = P[tri(c, c)];
-            sm[(long long)(24 + c) * N] = (Real)sqrt(acc_get(c) * invT);
-            sm[(long long)(36 + c) * N] = (Real)sqrt(acc_get(12 + c) * invT);
+            st_traj(prm.summary, (long long)c * N + i, x[c]);
+            st_traj(prm.summary, (long long)(12 + c) * N + i, P[tri(c, c)]);
+            st_traj(prm.summary, (long long)(24 + c) * N + i, rms_out(acc_get(c), invT, Real()));
+            st_traj(prm.summary, (long long)(36 + c) * N + i, rms_out(acc_get(12 + c), invT, Real()));
         }
-        sm[48LL * N] = (Real)(acc_get(24) * invT);
-        sm[49LL * N] = ptrace;
-        sm[50LL * N] = kgain;
-        sm[51LL * N] = (Real)sqrt((double)ymax);
+        st_traj(prm.summary, 48LL * N + i, mean_out(acc_get(24), invT, Real()));
+        st_traj(prm.summary, 49LL * N + i, ptrace);
+        st_traj(prm.summary, 50LL * N + i, kgain);
+        st_traj(prm.summary, 51LL * N + i, sqrt_(ymax));
     }
-    if (prm.status) prm.status[i] = status | (prm.stream_status ? prm.stream_status[s_warp + lane] : 0u);
+    if (prm.status) {
+#pragma unroll
+        for (int ln = 0; ln < L; ++ln)
+            prm.status[i + ln] = status[ln] | (prm.stream_status ? prm.stream_status[s_warp + lane * L + ln] : 0u);
+    }
 }
 
 }  // namespace okf

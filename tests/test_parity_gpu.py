@@ -267,3 +267,37 @@ def test_streamed_tma_kernel_matches_oracle_and_direct_kernel(dtype, tol):
     c = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], n_traj=N, dtype=dtype, outputs=("x_final",))
     flags = c.status.cpu().numpy() & 4
     assert flags[130] and flags.sum() // 4 == 1 + (1 if 130 + S < N else 0)
+
+
+def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
+    """FP32 with an even trajectory count and 64-stream tiles runs two trajectories per thread on FFMA2/FADD2/FMUL2
+    (the F2 instantiation).  It must agree with the one-trajectory-per-thread FP32 kernel to FP32 rounding and with
+    the FP64 oracle within the stated FP32 tolerance, including ragged last blocks and the status words."""
+    from optistate_b200.synth import monte_carlo_noise
+
+    S, T, N = 128, 300, 1000 + 2 * 37  # not a multiple of 256: the last block is ragged
+    st = make_streams(range(500, 500 + S), T)
+    st["contact"][40, :, 70] = 0.0  # one all-swing step on stream 70
+    q, r = monte_carlo_noise(np.arange(N), np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT))
+    rng = np.random.default_rng(9)
+    x0 = cases.START[:, None] + 0.01 * rng.standard_normal((12, N))
+    outs = ("x_steps", "p_trace", "k_gain", "nis", "final", "summary", "p_world_steps", "x_model_steps")
+    kw = dict(Q=q, R=r, x0=x0, n_traj=N, dtype=torch.float32, outputs=outs, truth=st["truth"], nominal=0.5 * st["truth"], stream_offset=64)
+    packed = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
+    monkeypatch.setenv("OPTISTATE_KF_NO_PACKED", "1")
+    scalar = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
+    monkeypatch.delenv("OPTISTATE_KF_NO_PACKED")
+    idx = ((np.arange(N) + 64) % S).astype(np.int32)
+    ref = c_oracle.run(st, N, Q=q, R=r, x0=x0, stream_index=idx, want=("x_steps", "p_trace_steps", "k_gain_steps", "P_final"))
+    scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
+    for res in (packed, scalar):
+        x = res.x_steps.cpu().numpy().astype(np.float64)
+        assert (np.abs(x - ref["x_steps"]).max(axis=(0, 2)) / scale).max() < parity.FP32_TOL_X
+        assert parity.rel_err(res.P_final.cpu().numpy(), ref["P_final"]) < parity.FP32_TOL_P
+        assert parity.rel_err(res.p_trace_steps.cpu().numpy(), ref["p_trace_steps"]) < parity.FP32_TOL_TRACE
+        assert parity.rel_err(res.k_gain_steps.cpu().numpy(), ref["k_gain_steps"]) < parity.FP32_TOL_TRACE
+    for name in outs[:3] + ("x_final", "P_final", "p_world_steps", "x_model_steps"):
+        name = {"p_trace": "p_trace_steps", "k_gain": "k_gain_steps"}.get(name, name)
+        assert parity.rel_err(packed.tensors[name].cpu().numpy(), scalar.tensors[name].cpu().numpy()) < 2e-5, name
+    assert parity.rel_err(packed.summary.cpu().numpy(), scalar.summary.cpu().numpy()) < 1e-4
+    assert torch.equal(packed.status, scalar.status) and int((packed.status & 4).sum()) // 4 == int((idx == 70).sum())
