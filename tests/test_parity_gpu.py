@@ -283,10 +283,11 @@ def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
     x0 = cases.START[:, None] + 0.01 * rng.standard_normal((12, N))
     outs = ("x_steps", "p_trace", "k_gain", "nis", "final", "summary", "p_world_steps", "x_model_steps")
     kw = dict(Q=q, R=r, x0=x0, n_traj=N, dtype=torch.float32, outputs=outs, truth=st["truth"], nominal=0.5 * st["truth"], stream_offset=64)
+    monkeypatch.setenv("OPTISTATE_KF_PACKED", "1")
     packed = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
-    monkeypatch.setenv("OPTISTATE_KF_NO_PACKED", "1")
+    monkeypatch.setenv("OPTISTATE_KF_PACKED", "0")
     scalar = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
-    monkeypatch.delenv("OPTISTATE_KF_NO_PACKED")
+    monkeypatch.delenv("OPTISTATE_KF_PACKED")
     idx = ((np.arange(N) + 64) % S).astype(np.int32)
     ref = c_oracle.run(st, N, Q=q, R=r, x0=x0, stream_index=idx, want=("x_steps", "p_trace_steps", "k_gain_steps", "P_final"))
     scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
