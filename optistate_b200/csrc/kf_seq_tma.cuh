@@ -157,19 +157,25 @@ __device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
 }
 
 // Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
+// Feet and forces are read leg by leg straight from the warp's shared-memory tile (`pin`, `fin`: channel stride 32)
+// so that at most one leg is live in registers; `pw_out` (optional) receives the feet rotated into the world frame.
 template <typename Real, typename Scalar>
-__device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm, Real (&x)[NX], Real (&p)[12], const Real (&f)[12],
-                                                      const Real (&R)[9], bool any_trunc) {
+__device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm, Real (&x)[NX], const Real *pin, const Real *fin,
+                                                      const Real (&R)[9], bool any_trunc, Scalar *pw_out, long long pw_idx, long long pw_stride) {
     constexpr int L = Lanes<Real>::n;
     Real tau[3] = {Real(0), Real(0), Real(0)}, fs[3] = {Real(0), Real(0), Real(0)};
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        const Real a = p[3 * l], b = p[3 * l + 1], c = p[3 * l + 2];
+        const Real a = pin[(3 * l) * 32], b = pin[(3 * l + 1) * 32], c = pin[(3 * l + 2) * 32];
         const Real pw0 = fma_(R[2], c, fma_(R[1], b, R[0] * a));
         const Real pw1 = fma_(R[5], c, fma_(R[4], b, R[3] * a));
         const Real pw2 = fma_(R[8], c, fma_(R[7], b, R[6] * a));
-        p[3 * l] = pw0; p[3 * l + 1] = pw1; p[3 * l + 2] = pw2;
-        const Real f0 = f[3 * l], f1 = f[3 * l + 1], f2 = f[3 * l + 2];
+        if (pw_out) {
+            st_traj(pw_out, pw_idx + (3 * l) * pw_stride, pw0);
+            st_traj(pw_out, pw_idx + (3 * l + 1) * pw_stride, pw1);
+            st_traj(pw_out, pw_idx + (3 * l + 2) * pw_stride, pw2);
+        }
+        const Real f0 = fin[(3 * l) * 32], f1 = fin[(3 * l + 1) * 32], f2 = fin[(3 * l + 2) * 32];
         tau[0] += fnma_(pw2, f1, pw1 * f2);
         tau[1] += fnma_(pw0, f2, pw2 * f0);
         tau[2] += fnma_(pw1, f0, pw0 * f1);
@@ -302,21 +308,13 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
 
         // ---- G0: feet and forces -> mean model --------------------------------------------------------------
         mbar_wait(&bars[0], par);
-        Real pf[12], ff[12];
-#pragma unroll
-        for (int c = 0; c < 12; ++c) { pf[c] = g0w[c * 32 + lane]; ff[c] = g0w[(12 + c) * 32 + lane]; }
-        __syncwarp();
+        propagate_mean_with_R(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc, active ? prm.p_world_steps : nullptr,
+                              (t * 12) * N + i, N);
+        __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
         if (more) issue_g0(maps, t + 1, s_warp, g0w, &bars[0], lane);
-        propagate_mean_with_R(prm, x, pf, ff, Rm, any_trunc);
-        if (active) {
-            if (prm.x_model_steps) {
+        if (active && prm.x_model_steps) {
 #pragma unroll
-                for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
-            }
-            if (prm.p_world_steps) {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) st_traj(prm.p_world_steps, (t * 12 + c) * N + i, pf[c]);
-            }
+            for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
         }
 
         cov_predict_sym(P, Rm, prm.dt, q, nt);
