@@ -155,6 +155,32 @@ typedef struct OptiKfMeasureDesc {
     uint32_t *status;                   /* [S] optional, OPTI_KF_ST_ALL_SWING */
 } OptiKfMeasureDesc;
 
+/* ---- next row after the filter: feature rows, min-max normalisation and sliding windows for the GRU consumer ---- */
+#define OPTI_KF_FEATURES 60 /* [x(12) imu_acc(6) f(12) p_world(12) dp(12) imu(6)], data_conversion_Kalman_to_Training.py:245-254 */
+
+typedef struct OptiKfFeatureDesc {
+    uint32_t struct_size, abi_version;
+    int32_t dtype, reserved;
+    int64_t n_traj, n_steps, n_streams, stream_offset;
+    const int32_t *stream_index;          /* [N] or NULL, same mapping as OptiKfDesc */
+    const void *x_steps, *p_world_steps;  /* [T][12][N] outputs of optistate_kf_batch */
+    const void *imu, *imu_acc, *f, *dp;   /* [T][6|6|12|12][S]; imu_acc (the driver's imu_list[i][6:12]) may be NULL = zeros */
+    void *rows;                           /* [N][T][60] row-major: the driver's state_INPUT rows per trajectory */
+} OptiKfFeatureDesc;
+
+/* Assembles the driver's 60-wide feature rows (replaces data_conversion_Kalman_to_Training.py:245-254). */
+int optistate_kf_features(const OptiKfFeatureDesc *desc, void *cuda_stream);
+/* Per-column minimum / maximum of a row-major [n_rows][n_cols] matrix (gru/gru_train.py:56-63); n_cols <= 256.
+ * `scratch` is device memory of at least optistate_kf_minmax_scratch_bytes(dtype, n_cols). */
+size_t optistate_kf_minmax_scratch_bytes(int dtype, int32_t n_cols);
+int optistate_kf_minmax(int dtype, const void *rows, int64_t n_rows, int32_t n_cols, void *min_out, void *max_out, void *scratch,
+                        size_t scratch_bytes, void *cuda_stream);
+/* (v - min) / (max - min) in `dtype`, `n_latent` float32 latent columns appended, sliding windows of seq_len rows inside
+ * each of the n_groups row groups, cast to float32 (gru/gru_train.py:108-111,180-192):
+ * out [n_groups][rows_per_group - seq_len + 1][seq_len][n_cols + n_latent].  latent may be NULL iff n_latent == 0. */
+int optistate_kf_windows(int dtype, const void *rows, const float *latent, const void *min, const void *max, int64_t n_groups,
+                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *cuda_stream);
+
 /* Runs the filter; dtype taken from the descriptor. */
 int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);
 /* Same, asserting the scalar type (the two names a binding would import). */

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "kf_features.cuh"
 #include "kf_joint.cuh"
 #include "kf_seq.cuh"
 #include "kf_seq_tma.cuh"
@@ -382,6 +383,74 @@ int optistate_fma_peak(int dtype, int64_t fma_per_thread, double *flops_per_s_ou
     if (dtype == OPTI_KF_F64) return fma_peak<double>(fma_per_thread, flops_per_s_out, seconds_out, stream);
     if (dtype == OPTI_KF_F32) return fma_peak<float>(fma_per_thread, flops_per_s_out, seconds_out, stream);
     return OPTI_KF_E_DTYPE;
+}
+
+int optistate_kf_features(const OptiKfFeatureDesc *d, void *cuda_stream) {
+    if (!d) return OPTI_KF_E_NULL;
+    if (d->struct_size != sizeof(OptiKfFeatureDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
+    if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (d->n_traj < 0 || d->n_steps < 0 || d->n_streams <= 0 || d->n_steps > 65535) return OPTI_KF_E_SHAPE;
+    if (!d->x_steps || !d->p_world_steps || !d->imu || !d->f || !d->dp || !d->rows) return OPTI_KF_E_NULL;
+    if (d->n_traj == 0 || d->n_steps == 0) return OPTI_KF_OK;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const dim3 grid((unsigned)((d->n_traj + 31) / 32), (unsigned)d->n_steps);
+    cudaGetLastError();
+    if (d->dtype == OPTI_KF_F64)
+        okf::kf_features_kernel<double><<<grid, 256, 0, stream>>>(d->n_traj, d->n_steps, d->n_streams, d->stream_offset, d->stream_index,
+                                                                  (const double *)d->x_steps, (const double *)d->p_world_steps,
+                                                                  (const double *)d->imu, (const double *)d->imu_acc, (const double *)d->f,
+                                                                  (const double *)d->dp, (double *)d->rows);
+    else
+        okf::kf_features_kernel<float><<<grid, 256, 0, stream>>>(d->n_traj, d->n_steps, d->n_streams, d->stream_offset, d->stream_index,
+                                                                 (const float *)d->x_steps, (const float *)d->p_world_steps,
+                                                                 (const float *)d->imu, (const float *)d->imu_acc, (const float *)d->f,
+                                                                 (const float *)d->dp, (float *)d->rows);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
+static const int kMinmaxBlocks = 592;
+
+size_t optistate_kf_minmax_scratch_bytes(int dtype, int32_t n_cols) {
+    return (size_t)kMinmaxBlocks * 2 * (size_t)(n_cols > 0 ? n_cols : 0) * (dtype == OPTI_KF_F64 ? 8 : 4);
+}
+
+int optistate_kf_minmax(int dtype, const void *rows, int64_t n_rows, int32_t n_cols, void *min_out, void *max_out, void *scratch,
+                        size_t scratch_bytes, void *cuda_stream) {
+    if (dtype != OPTI_KF_F64 && dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (!rows || !min_out || !max_out || !scratch) return OPTI_KF_E_NULL;
+    if (n_rows <= 0 || n_cols <= 0 || n_cols > 256 || scratch_bytes < optistate_kf_minmax_scratch_bytes(dtype, n_cols)) return OPTI_KF_E_SHAPE;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    cudaGetLastError();
+    if (dtype == OPTI_KF_F64) {
+        okf::kf_minmax_partial_kernel<double><<<kMinmaxBlocks, 256, 2 * 256 * sizeof(double), stream>>>((const double *)rows, n_rows, n_cols, (double *)scratch);
+        okf::kf_minmax_final_kernel<double><<<1, 256, 0, stream>>>((const double *)scratch, kMinmaxBlocks, n_cols, (double *)min_out, (double *)max_out);
+    } else {
+        okf::kf_minmax_partial_kernel<float><<<kMinmaxBlocks, 256, 2 * 256 * sizeof(float), stream>>>((const float *)rows, n_rows, n_cols, (float *)scratch);
+        okf::kf_minmax_final_kernel<float><<<1, 256, 0, stream>>>((const float *)scratch, kMinmaxBlocks, n_cols, (float *)min_out, (float *)max_out);
+    }
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
+int optistate_kf_windows(int dtype, const void *rows, const float *latent, const void *mn, const void *mx, int64_t n_groups,
+                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *cuda_stream) {
+    if (dtype != OPTI_KF_F64 && dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (!rows || !mn || !mx || !out || (n_latent > 0 && !latent)) return OPTI_KF_E_NULL;
+    if (n_groups <= 0 || n_groups > 65535 || seq_len <= 0 || rows_per_group < seq_len || n_cols <= 0 || n_latent < 0) return OPTI_KF_E_SHAPE;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const long long n_win = rows_per_group - seq_len + 1;
+    if (n_win >= (1LL << 31)) return OPTI_KF_E_SHAPE;
+    const dim3 grid((unsigned)n_win, (unsigned)n_groups);
+    cudaGetLastError();
+    if (dtype == OPTI_KF_F64)
+        okf::kf_windows_kernel<double><<<grid, 256, 0, stream>>>((const double *)rows, latent, (const double *)mn, (const double *)mx,
+                                                                 rows_per_group, n_cols, n_latent, seq_len, out);
+    else
+        okf::kf_windows_kernel<float><<<grid, 256, 0, stream>>>((const float *)rows, latent, (const float *)mn, (const float *)mx,
+                                                                rows_per_group, n_cols, n_latent, seq_len, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 
 const char *optistate_kf_strerror(int code) {

@@ -193,6 +193,74 @@ int kf_measure(int64_t dtype, int64_t n_steps, int64_t n_streams, const TensorMa
     return optistate_kf_measure(&d, at::cuda::getCurrentCUDAStream().stream());
 }
 
+// feature rows [N][T][60] from the filter outputs and the base streams
+int kf_features(int64_t dtype, int64_t n_traj, int64_t n_steps, int64_t n_streams, int64_t stream_offset, const TensorMap &tensors) {
+    OptiKfFeatureDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = (int32_t)dtype;
+    d.n_traj = n_traj; d.n_steps = n_steps; d.n_streams = n_streams; d.stream_offset = stream_offset;
+    auto xs = tensors.find("x_steps");
+    TORCH_CHECK(xs != tensors.end() && xs->second.is_cuda(), "optistate_b200: 'x_steps' must be a CUDA tensor (there is no CPU path)");
+    const Checker ck{dtype == OPTI_KF_F64 ? at::kDouble : at::kFloat, xs->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    const int64_t N = n_traj, T = n_steps, S = n_streams;
+    d.x_steps = ck.get(tensors, "x_steps", T * 12 * N, true);
+    d.p_world_steps = ck.get(tensors, "p_world_steps", T * 12 * N, true);
+    d.imu = ck.get(tensors, "imu", T * 6 * S, true);
+    d.imu_acc = ck.get(tensors, "imu_acc", T * 6 * S, false);
+    d.f = ck.get(tensors, "f", T * 12 * S, true);
+    d.dp = ck.get(tensors, "dp", T * 12 * S, true);
+    d.rows = const_cast<void *>(ck.get(tensors, "rows", N * T * OPTI_KF_FEATURES, true));
+    auto it = tensors.find("stream_index");
+    if (it != tensors.end()) {
+        const at::Tensor &t = it->second;
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == N, "optistate_b200: bad 'stream_index'");
+        d.stream_index = t.data_ptr<int32_t>();
+    }
+    return optistate_kf_features(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
+int kf_minmax(const at::Tensor &rows, at::Tensor mn, at::Tensor mx) {
+    TORCH_CHECK(rows.is_cuda() && rows.dim() == 2 && rows.is_contiguous(), "optistate_b200: rows must be a contiguous 2-D CUDA tensor");
+    TORCH_CHECK(rows.scalar_type() == at::kDouble || rows.scalar_type() == at::kFloat, "optistate_b200: rows must be float64 or float32");
+    TORCH_CHECK(mn.is_cuda() && mx.is_cuda() && mn.scalar_type() == rows.scalar_type() && mx.scalar_type() == rows.scalar_type() &&
+                    mn.numel() == rows.size(1) && mx.numel() == rows.size(1) && mn.is_contiguous() && mx.is_contiguous(),
+                "optistate_b200: min/max must be CUDA vectors of n_cols elements");
+    const c10::cuda::CUDAGuard guard(rows.device());
+    const int dtype = rows.scalar_type() == at::kDouble ? OPTI_KF_F64 : OPTI_KF_F32;
+    const size_t nb = optistate_kf_minmax_scratch_bytes(dtype, (int32_t)rows.size(1));
+    at::Tensor scratch = at::empty({(int64_t)nb}, rows.options().dtype(at::kByte));
+    return optistate_kf_minmax(dtype, rows.data_ptr(), rows.size(0), (int32_t)rows.size(1), mn.data_ptr(), mx.data_ptr(), scratch.data_ptr(), nb,
+                               at::cuda::getCurrentCUDAStream().stream());
+}
+
+int kf_windows(const at::Tensor &rows, const std::optional<at::Tensor> &latent, const at::Tensor &mn, const at::Tensor &mx, int64_t n_groups,
+               int64_t seq_len, at::Tensor out) {
+    TORCH_CHECK(rows.is_cuda() && rows.dim() == 2 && rows.is_contiguous(), "optistate_b200: rows must be a contiguous 2-D CUDA tensor");
+    TORCH_CHECK(rows.scalar_type() == at::kDouble || rows.scalar_type() == at::kFloat, "optistate_b200: rows must be float64 or float32");
+    TORCH_CHECK(n_groups > 0 && rows.size(0) % n_groups == 0, "optistate_b200: n_rows must be a multiple of n_groups");
+    const int64_t rpg = rows.size(0) / n_groups, cols = rows.size(1);
+    int64_t n_lat = 0;
+    const float *lat = nullptr;
+    if (latent.has_value()) {
+        const at::Tensor &l = *latent;
+        TORCH_CHECK(l.is_cuda() && l.scalar_type() == at::kFloat && l.is_contiguous() && l.dim() == 2 && l.size(0) == rows.size(0),
+                    "optistate_b200: latent must be a contiguous float32 CUDA tensor [n_rows, n_latent]");
+        n_lat = l.size(1);
+        lat = l.data_ptr<float>();
+    }
+    TORCH_CHECK(mn.is_cuda() && mx.is_cuda() && mn.scalar_type() == rows.scalar_type() && mx.scalar_type() == rows.scalar_type() &&
+                    mn.numel() == cols && mx.numel() == cols, "optistate_b200: bad min/max");
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.is_contiguous() &&
+                    out.numel() == n_groups * (rpg - seq_len + 1) * seq_len * (cols + n_lat), "optistate_b200: bad out");
+    const c10::cuda::CUDAGuard guard(rows.device());
+    return optistate_kf_windows(rows.scalar_type() == at::kDouble ? OPTI_KF_F64 : OPTI_KF_F32, rows.data_ptr(), lat, mn.data_ptr(), mx.data_ptr(),
+                                n_groups, rpg, (int32_t)cols, (int32_t)n_lat, (int32_t)seq_len, out.data_ptr<float>(),
+                                at::cuda::getCurrentCUDAStream().stream());
+}
+
 std::pair<double, double> fma_peak(int64_t dtype, int64_t fma_per_thread) {
     double flops = 0, secs = 0;
     const int rc = optistate_fma_peak((int)dtype, fma_per_thread, &flops, &secs, at::cuda::getCurrentCUDAStream().stream());
@@ -208,6 +276,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_measure", &kf_measure);
     m.def("kf_resolve_algo", &kf_resolve_algo);
     m.def("fma_peak", &fma_peak);
+    m.def("kf_features", &kf_features);
+    m.def("kf_minmax", &kf_minmax);
+    m.def("kf_windows", &kf_windows);
     m.def("strerror", [](int rc) { return std::string(optistate_kf_strerror(rc)); });
     m.def("launch_count", []() { return optistate_kf_launch_count(); });
     m.def("abi_version", []() { return optistate_kf_abi_version(); });

@@ -59,7 +59,11 @@ def make_stream(seed: int, n_steps: int) -> dict[str, np.ndarray]:
     truth = np.zeros((n_steps, 12))
     truth[:, 0:3] = (0.05 * np.sin(np.pi * t))[:, None]
     truth[:, 5] = 0.28
-    return {"imu": imu, "p": p, "dp": dp, "contact": contact, "f": f, "truth": truth}
+    # accelerometer channels of the recordings (imu_list[i][6:12], only copied into the GRU feature rows by the driver,
+    # data_conversion_Kalman_to_Training.py:246-247); drawn from a separate generator so the filter inputs above are unchanged
+    rng_acc = np.random.default_rng([seed, 1])
+    imu_acc = np.array([0.0, 0.0, GRAVITY, 0.0, 0.0, 0.0])[None, :] + 0.2 * rng_acc.standard_normal((n_steps, 6))
+    return {"imu": imu, "p": p, "dp": dp, "contact": contact, "f": f, "truth": truth, "imu_acc": imu_acc}
 
 
 def make_streams(seeds, n_steps: int) -> dict[str, np.ndarray]:

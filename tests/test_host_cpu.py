@@ -99,3 +99,26 @@ def test_noise_argument_classification_needs_no_gpu():
     assert _noise(np.ones((144, 5)), 12, 5, "P0", torch.float64, cpu)[1] == nv.MAT_DENSE_PER
     with pytest.raises(ValueError):
         _noise(np.ones((7, 3)), 12, 5, "Q", torch.float64, cpu)
+
+
+def test_gru_pipeline_restatement_shapes_and_reference_model_compatibility():
+    """The consumer restated in oracle/gru_pipeline.py has the reference RNN's parameter layout; when the reference tree is
+    present (build container) the two classes produce identical outputs from the same state_dict."""
+    from oracle import gru_pipeline, ref_shim
+
+    rows = np.random.default_rng(0).standard_normal((50, 60))
+    norm, lo, hi = gru_pipeline.min_max_normalise(rows)
+    assert norm.min() == 0.0 and norm.max() == 1.0
+    w = gru_pipeline.windows(norm, gru_pipeline.seeded_latent(50))
+    assert w.shape == (41, 10, 188) and w.dtype == np.float32 and np.array_equal(w[3, 2, :60], norm[5].astype(np.float32))
+    model = gru_pipeline.seeded_consumer()
+    assert sum(p.numel() for p in model.parameters()) == 422424  # SURVEY 2: gru_model.RNN(188,128,4,24)
+    if ref_shim.available():
+        sys.path.insert(0, ref_shim.REF_ROOT)
+        from gru.gru_model import RNN
+
+        ref_model = RNN(188, 128, 4, 24, torch.device("cpu")).eval()
+        ref_model.load_state_dict(model.state_dict())
+        x = torch.from_numpy(w)
+        with torch.no_grad():
+            assert torch.equal(ref_model(x), model(x))
