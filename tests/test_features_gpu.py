@@ -38,12 +38,14 @@ def test_feature_rows_minmax_windows_are_exact_data_movement(dtype):
     w1 = normalized_windows(flat, lo, hi, latent, n_groups=1, seq_len=10)
     norm = ((want.reshape(-1, 60) - want.reshape(-1, 60).min(axis=0)) / (want.reshape(-1, 60).max(axis=0) - want.reshape(-1, 60).min(axis=0)))
     ref1 = np.stack([np.concatenate([norm, latent.cpu().numpy().astype(npdt)], axis=1)[i:i + 10] for i in range(N * T - 9)]).astype(np.float32)
-    assert w1.shape == (1, N * T - 9, 10, 188) and np.array_equal(w1[0].cpu().numpy(), ref1)
+    assert w1.shape == (1, N * T - 9, 10, 188) and np.array_equal(w1[0].cpu().numpy(), ref1, equal_nan=True)
+    assert np.isnan(ref1[0, 0, 18]) and not np.isnan(ref1[..., 20]).any()  # constant columns (f_x = 0) give 0/0 exactly as in NumPy
     wn = normalized_windows(flat, lo, hi, latent, n_groups=N, seq_len=10)
     assert wn.shape == (N, T - 9, 10, 188)
-    assert np.array_equal(wn[3, 5].cpu().numpy(), ref1[3 * T + 5]) and np.array_equal(wn[N - 1, T - 10].cpu().numpy(), ref1[(N - 1) * T + T - 10])
+    assert np.array_equal(wn[3, 5].cpu().numpy(), ref1[3 * T + 5], equal_nan=True)
+    assert np.array_equal(wn[N - 1, T - 10].cpu().numpy(), ref1[(N - 1) * T + T - 10], equal_nan=True)
     w0 = normalized_windows(flat, lo, hi, None, n_groups=N, seq_len=4)
-    assert w0.shape == (N, T - 3, 4, 60) and np.array_equal(w0[1, 0].cpu().numpy(), ref1[T][:4, :60])
+    assert w0.shape == (N, T - 3, 4, 60) and np.array_equal(w0[1, 0].cpu().numpy(), ref1[T][:4, :60], equal_nan=True)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 2e-6), (torch.float32, 2e-4)])
@@ -52,6 +54,8 @@ def test_config5_gru_rmse_parity_batched_kf_vs_reference_kf(dtype, tol):
     filter (oracle port), same seeded weights and latents.  The GRU itself runs in float32 in both arms."""
     S, T = 4, 400
     st = make_streams(range(80, 80 + S), T)
+    # the synthetic forces have f_x = f_y = 0 (constant columns would normalise to 0/0): give them a small lateral component
+    st["f"][:, [0, 1, 3, 4, 6, 7, 9, 10], :] = 0.5 * np.random.default_rng(3).standard_normal((T, 8, S))
     ref = c_oracle.run(st, want=("x_steps", "p_world_steps"))
     rows_ref = numpy_rows(ref["x_steps"], ref["p_world_steps"], st, np.arange(S)).reshape(-1, 60)
     norm_ref, _, _ = gru_pipeline.min_max_normalise(rows_ref)
