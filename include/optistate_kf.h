@@ -177,9 +177,13 @@ int optistate_kf_minmax(int dtype, const void *rows, int64_t n_rows, int32_t n_c
                         size_t scratch_bytes, void *cuda_stream);
 /* (v - min) / (max - min) in `dtype`, `n_latent` float32 latent columns appended, sliding windows of seq_len rows inside
  * each of the n_groups row groups, cast to float32 (gru/gru_train.py:108-111,180-192):
- * out [n_groups][rows_per_group - seq_len + 1][seq_len][n_cols + n_latent].  latent may be NULL iff n_latent == 0. */
+ * out [n_groups][rows_per_group - seq_len + 1][seq_len][n_cols + n_latent].  latent may be NULL iff n_latent == 0.
+ * Every row is normalised once into `scratch` (device memory, optistate_kf_windows_scratch_bytes), then each window is a
+ * contiguous copy of seq_len rows. */
+size_t optistate_kf_windows_scratch_bytes(int64_t n_groups, int64_t rows_per_group, int32_t n_cols, int32_t n_latent);
 int optistate_kf_windows(int dtype, const void *rows, const float *latent, const void *min, const void *max, int64_t n_groups,
-                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *cuda_stream);
+                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *scratch,
+                         size_t scratch_bytes, void *cuda_stream);
 
 /* Runs the filter; dtype taken from the descriptor. */
 int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);

@@ -393,7 +393,7 @@ int optistate_kf_features(const OptiKfFeatureDesc *d, void *cuda_stream) {
     if (!d->x_steps || !d->p_world_steps || !d->imu || !d->f || !d->dp || !d->rows) return OPTI_KF_E_NULL;
     if (d->n_traj == 0 || d->n_steps == 0) return OPTI_KF_OK;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const dim3 grid((unsigned)((d->n_traj + 31) / 32), (unsigned)d->n_steps);
+    const dim3 grid((unsigned)((d->n_traj + okf::FEAT_TRAJ - 1) / okf::FEAT_TRAJ), (unsigned)((d->n_steps + okf::FEAT_STEPS - 1) / okf::FEAT_STEPS));
     cudaGetLastError();
     if (d->dtype == OPTI_KF_F64)
         okf::kf_features_kernel<double><<<grid, 256, 0, stream>>>(d->n_traj, d->n_steps, d->n_streams, d->stream_offset, d->stream_index,
@@ -433,23 +433,36 @@ int optistate_kf_minmax(int dtype, const void *rows, int64_t n_rows, int32_t n_c
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 
+size_t optistate_kf_windows_scratch_bytes(int64_t n_groups, int64_t rows_per_group, int32_t n_cols, int32_t n_latent) {
+    if (n_groups <= 0 || rows_per_group <= 0 || n_cols <= 0 || n_latent < 0) return 0;
+    return (size_t)n_groups * (size_t)rows_per_group * (size_t)(n_cols + n_latent) * sizeof(float);
+}
+
 int optistate_kf_windows(int dtype, const void *rows, const float *latent, const void *mn, const void *mx, int64_t n_groups,
-                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *cuda_stream) {
+                         int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *scratch,
+                         size_t scratch_bytes, void *cuda_stream) {
     if (dtype != OPTI_KF_F64 && dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
-    if (!rows || !mn || !mx || !out || (n_latent > 0 && !latent)) return OPTI_KF_E_NULL;
-    if (n_groups <= 0 || n_groups > 65535 || seq_len <= 0 || rows_per_group < seq_len || n_cols <= 0 || n_latent < 0) return OPTI_KF_E_SHAPE;
+    if (!rows || !mn || !mx || !out || !scratch || (n_latent > 0 && !latent)) return OPTI_KF_E_NULL;
+    if (n_groups <= 0 || seq_len <= 0 || rows_per_group < seq_len || n_cols <= 0 || n_latent < 0) return OPTI_KF_E_SHAPE;
+    if (scratch_bytes < optistate_kf_windows_scratch_bytes(n_groups, rows_per_group, n_cols, n_latent)) return OPTI_KF_E_SHAPE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const long long n_win = rows_per_group - seq_len + 1;
-    if (n_win >= (1LL << 31)) return OPTI_KF_E_SHAPE;
-    const dim3 grid((unsigned)n_win, (unsigned)n_groups);
+    const long long n_rows = n_groups * rows_per_group;
+    const int width = n_cols + n_latent;
+    float *full = (float *)scratch;
     cudaGetLastError();
+    const unsigned nb = 148 * 16;
     if (dtype == OPTI_KF_F64)
-        okf::kf_windows_kernel<double><<<grid, 256, 0, stream>>>((const double *)rows, latent, (const double *)mn, (const double *)mx,
-                                                                 rows_per_group, n_cols, n_latent, seq_len, out);
+        okf::kf_normalise_rows_kernel<double><<<nb, 256, 0, stream>>>((const double *)rows, latent, (const double *)mn, (const double *)mx,
+                                                                      n_rows, n_cols, n_latent, full);
     else
-        okf::kf_windows_kernel<float><<<grid, 256, 0, stream>>>((const float *)rows, latent, (const float *)mn, (const float *)mx,
-                                                                rows_per_group, n_cols, n_latent, seq_len, out);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+        okf::kf_normalise_rows_kernel<float><<<nb, 256, 0, stream>>>((const float *)rows, latent, (const float *)mn, (const float *)mx, n_rows,
+                                                                     n_cols, n_latent, full);
+    const bool vec4 = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(full) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (vec4)
+        okf::kf_windows_copy_kernel<float4><<<nb, 256, 0, stream>>>((const float4 *)full, rows_per_group, n_groups, width / 4, seq_len, (float4 *)out);
+    else
+        okf::kf_windows_copy_kernel<float><<<nb, 256, 0, stream>>>(full, rows_per_group, n_groups, width, seq_len, out);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 

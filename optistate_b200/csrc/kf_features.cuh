@@ -16,37 +16,42 @@ namespace okf {
 
 constexpr int FEAT = 60;
 
-// block = 32 trajectories x 1 step; 256 threads.  Loads are coalesced along the trajectory index (SoA inputs),
-// stores are row-contiguous (60 values per trajectory row).
+// block = 64 trajectories x FEAT_STEPS steps; 256 threads.  Loads are coalesced along the trajectory index (SoA
+// inputs, 64 consecutive values per channel), stores are row-contiguous (60 values per trajectory row).
+constexpr int FEAT_TRAJ = 64, FEAT_STEPS = 4;
+
 template <typename Real>
 __global__ void __launch_bounds__(256) kf_features_kernel(long long N, long long T, long long S, long long stream_offset,
                                                            const int32_t *__restrict__ stream_index, const Real *__restrict__ x_steps,
                                                            const Real *__restrict__ p_world, const Real *__restrict__ imu,
                                                            const Real *__restrict__ imu_acc, const Real *__restrict__ f,
                                                            const Real *__restrict__ dp, Real *__restrict__ rows) {
-    __shared__ Real tile[FEAT][33];
-    const long long t = blockIdx.y;
-    const long long i0 = (long long)blockIdx.x * 32;
-    for (int e = threadIdx.x; e < FEAT * 32; e += blockDim.x) {
-        const int c = e / 32, li = e % 32;
-        const long long i = i0 + li;
-        Real v = Real(0);
-        if (i < N) {
-            const long long s = stream_index ? (long long)stream_index[i] : (i + stream_offset) % S;
-            if (c < 12) v = x_steps[(t * 12 + c) * N + i];
-            else if (c < 18) v = imu_acc ? imu_acc[(t * 6 + (c - 12)) * S + s] : Real(0);
-            else if (c < 30) v = f[(t * 12 + (c - 18)) * S + s];
-            else if (c < 42) v = p_world[(t * 12 + (c - 30)) * N + i];
-            else if (c < 54) v = dp[(t * 12 + (c - 42)) * S + s];
-            else v = imu[(t * 6 + (c - 54)) * S + s];
+    __shared__ Real tile[FEAT][FEAT_TRAJ + 1];
+    const long long i0 = (long long)blockIdx.x * FEAT_TRAJ;
+    const int li_ld = threadIdx.x % FEAT_TRAJ, c_ld0 = threadIdx.x / FEAT_TRAJ;  // 4 channels in flight per pass
+    const long long i_ld = i0 + li_ld;
+    const long long s_ld = i_ld < N ? (stream_index ? (long long)stream_index[i_ld] : (i_ld + stream_offset) % S) : 0;
+    for (long long t = (long long)blockIdx.y * FEAT_STEPS; t < T && t < ((long long)blockIdx.y + 1) * FEAT_STEPS; ++t) {
+#pragma unroll 5
+        for (int c = c_ld0; c < FEAT; c += 256 / FEAT_TRAJ) {
+            Real v = Real(0);
+            if (i_ld < N) {
+                if (c < 12) v = x_steps[(t * 12 + c) * N + i_ld];
+                else if (c < 18) v = imu_acc ? imu_acc[(t * 6 + (c - 12)) * S + s_ld] : Real(0);
+                else if (c < 30) v = f[(t * 12 + (c - 18)) * S + s_ld];
+                else if (c < 42) v = p_world[(t * 12 + (c - 30)) * N + i_ld];
+                else if (c < 54) v = dp[(t * 12 + (c - 42)) * S + s_ld];
+                else v = imu[(t * 6 + (c - 54)) * S + s_ld];
+            }
+            tile[c][li_ld] = v;
         }
-        tile[c][li] = v;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < FEAT * 32; e += blockDim.x) {
-        const int li = e / FEAT, c = e % FEAT;
-        const long long i = i0 + li;
-        if (i < N) rows[(i * T + t) * FEAT + c] = tile[c][li];
+        __syncthreads();
+        for (int e = threadIdx.x; e < FEAT * FEAT_TRAJ; e += 256) {
+            const int li = e / FEAT, c = e % FEAT;
+            const long long i = i0 + li;
+            if (i < N) __stcs(rows + (i * T + t) * FEAT + c, tile[c][li]);
+        }
+        __syncthreads();
     }
 }
 
@@ -60,7 +65,16 @@ __global__ void __launch_bounds__(256) kf_minmax_partial_kernel(const Real *__re
     const int g = threadIdx.x / cols, c = threadIdx.x % cols;
     Real mn = Real(INFINITY), mx = Real(-INFINITY);
     if (g < groups) {
-        for (long long r = (long long)blockIdx.x * groups + g; r < n_rows; r += (long long)gridDim.x * groups) {
+        const long long stride = (long long)gridDim.x * groups;
+        long long r = (long long)blockIdx.x * groups + g;
+        for (; r + 3 * stride < n_rows; r += 4 * stride) {  // four independent loads in flight per thread
+            const Real v0 = __ldcs(rows + r * cols + c), v1 = __ldcs(rows + (r + stride) * cols + c);
+            const Real v2 = __ldcs(rows + (r + 2 * stride) * cols + c), v3 = __ldcs(rows + (r + 3 * stride) * cols + c);
+            const Real lo = fmin(fmin(v0, v1), fmin(v2, v3)), hi = fmax(fmax(v0, v1), fmax(v2, v3));
+            mn = lo < mn ? lo : mn;
+            mx = hi > mx ? hi : mx;
+        }
+        for (; r < n_rows; r += stride) {
             const Real v = rows[r * cols + c];
             mn = v < mn ? v : mn;
             mx = v > mx ? v : mx;
@@ -95,28 +109,39 @@ __global__ void kf_minmax_final_kernel(const Real *__restrict__ partial, int n_p
     mx_out[c] = mx;
 }
 
-// out[g][n][w][c] = c < cols ? float((rows[g][n+w][c] - mn[c]) / (mx[c] - mn[c])) : latent[g][n+w][c-cols]
-// one block per (g, n): seq * width consecutive floats, read from the L2-resident rows (each row is reused by `seq` windows)
+// full[r][c] = c < cols ? float((rows[r][c] - mn[c]) / (mx[c] - mn[c])) : latent[r][c - cols]      (each row normalised ONCE)
 template <typename Real>
-__global__ void __launch_bounds__(256) kf_windows_kernel(const Real *__restrict__ rows, const float *__restrict__ latent,
-                                                          const Real *__restrict__ mn, const Real *__restrict__ mx, long long rows_per_group,
-                                                          int cols, int n_latent, int seq, float *__restrict__ out) {
-    const long long n_win = rows_per_group - seq + 1;
-    const long long g = blockIdx.y, n = blockIdx.x;
-    if (n >= n_win) return;
+__global__ void __launch_bounds__(256) kf_normalise_rows_kernel(const Real *__restrict__ rows, const float *__restrict__ latent,
+                                                                 const Real *__restrict__ mn, const Real *__restrict__ mx, long long n_rows,
+                                                                 int cols, int n_latent, float *__restrict__ full) {
     const int width = cols + n_latent;
-    float *dst = out + ((g * n_win + n) * seq) * (long long)width;
-    const long long r0 = g * rows_per_group + n;
-    for (int e = threadIdx.x; e < seq * width; e += blockDim.x) {
-        const int w = e / width, c = e % width;
+    const long long total = n_rows * width;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / width;
+        const int c = (int)(e - r * width);
         float v;
         if (c < cols) {
             const Real lo = mn[c], hi = mx[c];
-            v = (float)((rows[(r0 + w) * cols + c] - lo) / (hi - lo));
+            v = (float)((rows[r * cols + c] - lo) / (hi - lo));
         } else {
-            v = latent[(r0 + w) * n_latent + (c - cols)];
+            v = latent[r * n_latent + (c - cols)];
         }
-        dst[e] = v;
+        full[e] = v;
+    }
+}
+
+// out[g][n] = full[g*rpg + n .. g*rpg + n + seq) : `seq` consecutive rows are one contiguous run of the normalised buffer,
+// so a window is a straight copy of seq*width floats.  Vec = float4 when width % 4 == 0, float otherwise.
+template <typename Vec>
+__global__ void __launch_bounds__(256) kf_windows_copy_kernel(const Vec *__restrict__ full, long long rows_per_group, long long n_groups,
+                                                               int row_vecs, int seq, Vec *__restrict__ out) {
+    const long long n_win = rows_per_group - seq + 1;
+    const long long win_vecs = (long long)seq * row_vecs;
+    const long long total = n_groups * n_win * win_vecs;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long w = e / win_vecs, off = e - w * win_vecs;
+        const long long g = w / n_win, n = w - g * n_win;
+        __stcs(out + e, full[(g * rows_per_group + n) * row_vecs + off]);
     }
 }
 

@@ -256,8 +256,10 @@ int kf_windows(const at::Tensor &rows, const std::optional<at::Tensor> &latent, 
     TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.is_contiguous() &&
                     out.numel() == n_groups * (rpg - seq_len + 1) * seq_len * (cols + n_lat), "optistate_b200: bad out");
     const c10::cuda::CUDAGuard guard(rows.device());
+    const size_t nb = optistate_kf_windows_scratch_bytes(n_groups, rpg, (int32_t)cols, (int32_t)n_lat);
+    at::Tensor scratch = at::empty({(int64_t)nb}, rows.options().dtype(at::kByte));
     return optistate_kf_windows(rows.scalar_type() == at::kDouble ? OPTI_KF_F64 : OPTI_KF_F32, rows.data_ptr(), lat, mn.data_ptr(), mx.data_ptr(),
-                                n_groups, rpg, (int32_t)cols, (int32_t)n_lat, (int32_t)seq_len, out.data_ptr<float>(),
+                                n_groups, rpg, (int32_t)cols, (int32_t)n_lat, (int32_t)seq_len, out.data_ptr<float>(), scratch.data_ptr(), nb,
                                 at::cuda::getCurrentCUDAStream().stream());
 }
 
