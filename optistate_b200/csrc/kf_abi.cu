@@ -459,9 +459,9 @@ int optistate_kf_windows(int dtype, const void *rows, const float *latent, const
                                                                      n_cols, n_latent, full);
     const bool vec4 = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(full) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
     if (vec4)
-        okf::kf_windows_copy_kernel<float4><<<nb, 256, 0, stream>>>((const float4 *)full, rows_per_group, n_groups, width / 4, seq_len, (float4 *)out);
+        okf::kf_windows_copy_kernel<float4><<<nb, dim3(64, 4), 0, stream>>>((const float4 *)full, rows_per_group, n_groups, width / 4, seq_len, (float4 *)out);
     else
-        okf::kf_windows_copy_kernel<float><<<nb, 256, 0, stream>>>(full, rows_per_group, n_groups, width, seq_len, out);
+        okf::kf_windows_copy_kernel<float><<<nb, dim3(64, 4), 0, stream>>>(full, rows_per_group, n_groups, width, seq_len, out);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }

@@ -65,16 +65,7 @@ __global__ void __launch_bounds__(256) kf_minmax_partial_kernel(const Real *__re
     const int g = threadIdx.x / cols, c = threadIdx.x % cols;
     Real mn = Real(INFINITY), mx = Real(-INFINITY);
     if (g < groups) {
-        const long long stride = (long long)gridDim.x * groups;
-        long long r = (long long)blockIdx.x * groups + g;
-        for (; r + 3 * stride < n_rows; r += 4 * stride) {  // four independent loads in flight per thread
-            const Real v0 = __ldcs(rows + r * cols + c), v1 = __ldcs(rows + (r + stride) * cols + c);
-            const Real v2 = __ldcs(rows + (r + 2 * stride) * cols + c), v3 = __ldcs(rows + (r + 3 * stride) * cols + c);
-            const Real lo = fmin(fmin(v0, v1), fmin(v2, v3)), hi = fmax(fmax(v0, v1), fmax(v2, v3));
-            mn = lo < mn ? lo : mn;
-            mx = hi > mx ? hi : mx;
-        }
-        for (; r < n_rows; r += stride) {
+        for (long long r = (long long)blockIdx.x * groups + g; r < n_rows; r += (long long)gridDim.x * groups) {
             const Real v = rows[r * cols + c];
             mn = v < mn ? v : mn;
             mx = v > mx ? v : mx;
@@ -135,13 +126,15 @@ __global__ void __launch_bounds__(256) kf_normalise_rows_kernel(const Real *__re
 template <typename Vec>
 __global__ void __launch_bounds__(256) kf_windows_copy_kernel(const Vec *__restrict__ full, long long rows_per_group, long long n_groups,
                                                                int row_vecs, int seq, Vec *__restrict__ out) {
+    // blockDim = (64, 4): each thread row copies one window per trip; no per-element index arithmetic
     const long long n_win = rows_per_group - seq + 1;
-    const long long win_vecs = (long long)seq * row_vecs;
-    const long long total = n_groups * n_win * win_vecs;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long w = e / win_vecs, off = e - w * win_vecs;
+    const int win_vecs = seq * row_vecs;
+    const long long total = n_groups * n_win;
+    for (long long w = (long long)blockIdx.x * blockDim.y + threadIdx.y; w < total; w += (long long)gridDim.x * blockDim.y) {
         const long long g = w / n_win, n = w - g * n_win;
-        __stcs(out + e, full[(g * rows_per_group + n) * row_vecs + off]);
+        const Vec *src = full + (g * rows_per_group + n) * row_vecs;
+        Vec *dst = out + w * win_vecs;
+        for (int off = threadIdx.x; off < win_vecs; off += blockDim.x) __stcs(dst + off, src[off]);
     }
 }
 
