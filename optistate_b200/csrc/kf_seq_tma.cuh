@@ -225,7 +225,23 @@ __global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_co
     constexpr int nt = TMA_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = prm.N, S = prm.S;
-    const long long i0 = (long long)blockIdx.x * nt * L;  // first trajectory of the block
+    // Trajectory block b reads stream tile b % n_tiles.  Launch order is permuted so that consecutive (= co-resident)
+    // blocks share ONE stream tile: its whole time series (tens of MB) then stays L2-resident no matter how far the
+    // resident blocks drift apart in time, instead of every block streaming its tile from HBM again (measured: 375 GB
+    // -> ~1 GB of DRAM reads per launch on the 1 M x 1 k sweep).
+    long long blk = blockIdx.x;
+    {
+        const long long per_block = (long long)nt * L;
+        const long long n_tiles = (S % per_block == 0) ? S / per_block : 1;
+        if (n_tiles > 1) {
+            const long long nb = gridDim.x, base = nb / n_tiles, rem = nb % n_tiles, q = blockIdx.x;
+            long long k, j;
+            if (q < rem * (base + 1)) { k = q / (base + 1); j = q % (base + 1); }
+            else { const long long q2 = q - rem * (base + 1); k = rem + q2 / base; j = q2 % base; }
+            blk = j * n_tiles + k;
+        }
+    }
+    const long long i0 = blk * nt * L;  // first trajectory of the block
     const long long i = i0 + (long long)tid * L;           // first trajectory of this thread
     const bool active = i < N;                             // N % L == 0 is guaranteed by the host
     const long long ic = active ? i : N - L;               // clamped index for per-trajectory parameter loads
