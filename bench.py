@@ -36,9 +36,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_ALGORITHMIC = 6800.0  # per trajectory-step, reference operand order, structural zeros skipped
-# flops the streamed SEQUENTIAL kernel actually executes per trajectory-step, counted from the SASS of its time loop
-# with ncu (profiles/r1_*): FP64 1110 DFMA + 321 DMUL + 76 DADD ; FP32 see DESIGN.md
-FLOPS_EXECUTED = {"f64": 2 * 1110 + 321 + 76, "f32": 2 * 1119 + 321 + 108}
+# flops the streamed SEQUENTIAL kernel actually executes per trajectory-step in this workload (summary on, two label
+# streams), counted by ncu in the SASS of its time loop (profiles/r1_ncu_bench_kernel_*_hotloop.txt):
+#   FP64: 1128 DFMA + 315 DMUL + 102 DADD;  FP32 (two trajectories per thread): (1031 FFMA2 + 302 FMUL2 + 97 FADD2)*2 lanes
+#   + 106 FFMA + 22 FADD + 12 FMUL per PAIR of trajectories
+FLOPS_EXECUTED = {"f64": 2 * 1128 + 315 + 102, "f32": (2 * 2 * 1031 + 2 * 302 + 2 * 97 + 2 * 106 + 22 + 12) / 2}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the ncu
+# captures under profiles/ (r1_ncu_bench_kernel_*_metrics.txt); None for any other workload shape
+TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 4.04e9 + 0.432e9}
+# algorithmic bytes of one launch: every base-stream channel read once (p, f, z, two label streams = 58 scalars per
+# stream-step) + 22 noise scalars in and 52 summary scalars out per trajectory
+def algorithmic_bytes(a, esz):
+    return (58 * a.T * a.streams + (22 + 52) * a.traj_per_gpu) * esz
 METRIC = "kf_trajectory_steps_per_sec"
 UNIT = "trajectory-steps/s"
 
@@ -324,7 +333,8 @@ def run_native(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
         "data": "synthetic", "config": workload_config(a, world), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {
-            "bound": "fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+            "bound": "fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+            "traffic": TRAFFIC_BYTES.get((a.dtype, a.traj_per_gpu, a.T, a.streams)), "algorithmic_bytes": algorithmic_bytes(a, esz),
             "note": f"per GPU; achieved = {int(FLOPS_ALGORITHMIC)} algorithmic flops/trajectory-step x steps/s; peak = {a.dtype} FMA issue peak "
                     "measured in this run (optistate_fma_peak); the kernel executes fewer flops than the algorithmic count "
                     "(sequential scalar updates on a packed symmetric P), hence frac can exceed 1 - see executed_*",
