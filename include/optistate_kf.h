@@ -185,6 +185,25 @@ int optistate_kf_windows(int dtype, const void *rows, const float *latent, const
                          int64_t rows_per_group, int32_t n_cols, int32_t n_latent, int32_t seq_len, float *out, void *scratch,
                          size_t scratch_bytes, void *cuda_stream);
 
+/* ---- step before the filter: the driver's Q / R identification pass (data_conversion_Kalman_to_Training.py:31-109) ---- */
+typedef struct OptiKfIdentifyDesc {
+    uint32_t struct_size, abi_version;
+    int32_t dtype;
+    int32_t alias_last_measurement;       /* 1: reproduce the driver's aliasing of KF.z (:74) - every stored measurement is the last one */
+    int64_t n_traj, n_steps, n_streams, stream_offset;
+    const int32_t *stream_index;          /* [N] or NULL, same mapping as OptiKfDesc */
+    double dt, mass, inertia[3], gravity;
+    const void *gt;                       /* [T][12][S] ground-truth (mocap) states */
+    const void *imu, *p, *dp, *contact, *f; /* [T][6|12|12|4|12][S]; f = the forces predict_mpc would apply at each step */
+    void *q_diag;                         /* [12][N] variance of gt[i+1] - next_state(gt[i], p[i], f[i]) */
+    void *r_diag;                         /* [10][N] variance of H gt[i+1] - z[i+1] */
+    uint32_t *status;                     /* [N] optional, pre-zeroed by the caller; OPTI_KF_ST_ALL_SWING */
+    void *scratch;                        /* device memory of optistate_kf_identify_scratch_bytes() */
+    size_t scratch_bytes;
+} OptiKfIdentifyDesc;
+size_t optistate_kf_identify_scratch_bytes(int dtype, int64_t n_traj, int64_t n_steps);
+int optistate_kf_identify_noise(const OptiKfIdentifyDesc *desc, void *cuda_stream);
+
 /* Runs the filter; dtype taken from the descriptor. */
 int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);
 /* Same, asserting the scalar type (the two names a binding would import). */

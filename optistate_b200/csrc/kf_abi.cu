@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "kf_features.cuh"
+#include "kf_identify.cuh"
 #include "kf_joint.cuh"
 #include "kf_seq.cuh"
 #include "kf_seq_tma.cuh"
@@ -316,6 +317,27 @@ int fma_peak(long long fma_per_thread, double *flops_out, double *seconds_out, c
     return OPTI_KF_OK;
 }
 
+template <typename Real>
+int identify_noise(const OptiKfIdentifyDesc *d, cudaStream_t stream) {
+    okf::Params<Real> p;
+    std::memset(&p, 0, sizeof p);
+    p.N = d->n_traj; p.T = d->n_steps; p.S = d->n_streams; p.stream_offset = d->stream_offset; p.stream_index = d->stream_index;
+    p.dt = (Real)d->dt;
+    p.dt_over_m = (Real)((1.0 / d->mass) * d->dt);
+    p.dt_g = (Real)(d->dt * d->gravity);
+    for (int k = 0; k < 3; ++k) p.inv_inertia[k] = (Real)(1.0 / d->inertia[k]);
+    p.imu = (const Real *)d->imu; p.p = (const Real *)d->p; p.dp = (const Real *)d->dp;
+    p.contact = (const Real *)d->contact; p.f = (const Real *)d->f; p.status = d->status;
+    const long long pairs = (d->n_steps - 1) * d->n_traj;
+    okf::kf_identify_residuals_kernel<Real><<<(unsigned)((pairs + 127) / 128), 128, 0, stream>>>(p, (const Real *)d->gt, d->alias_last_measurement,
+                                                                                                  (Real *)d->scratch);
+    const long long comps = (long long)okf::IDENT_ROWS * d->n_traj;
+    okf::kf_identify_variance_kernel<Real><<<(unsigned)((comps + 127) / 128), 128, 0, stream>>>(d->n_traj, d->n_steps - 1, (const Real *)d->scratch,
+                                                                                                 (Real *)d->q_diag, (Real *)d->r_diag);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
 }  // namespace
 
 extern "C" {
@@ -464,6 +486,24 @@ int optistate_kf_windows(int dtype, const void *rows, const float *latent, const
         okf::kf_windows_copy_kernel<float><<<nb, dim3(64, 4), 0, stream>>>(full, rows_per_group, n_groups, width, seq_len, out);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+}
+
+size_t optistate_kf_identify_scratch_bytes(int dtype, int64_t n_traj, int64_t n_steps) {
+    if (n_traj <= 0 || n_steps < 2) return 0;
+    return (size_t)(n_steps - 1) * okf::IDENT_ROWS * (size_t)n_traj * (dtype == OPTI_KF_F64 ? 8 : 4);
+}
+
+int optistate_kf_identify_noise(const OptiKfIdentifyDesc *d, void *cuda_stream) {
+    if (!d) return OPTI_KF_E_NULL;
+    if (d->struct_size != sizeof(OptiKfIdentifyDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
+    if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
+    if (d->n_traj <= 0 || d->n_steps < 2 || d->n_streams <= 0) return OPTI_KF_E_SHAPE;
+    if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0)) return OPTI_KF_E_SHAPE;
+    if (!d->gt || !d->imu || !d->p || !d->dp || !d->contact || !d->f || !d->q_diag || !d->r_diag || !d->scratch) return OPTI_KF_E_NULL;
+    if (d->scratch_bytes < optistate_kf_identify_scratch_bytes(d->dtype, d->n_traj, d->n_steps)) return OPTI_KF_E_SHAPE;
+    cudaGetLastError();
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    return d->dtype == OPTI_KF_F64 ? identify_noise<double>(d, stream) : identify_noise<float>(d, stream);
 }
 
 const char *optistate_kf_strerror(int code) {

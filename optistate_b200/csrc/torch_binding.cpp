@@ -263,6 +263,50 @@ int kf_windows(const at::Tensor &rows, const std::optional<at::Tensor> &latent, 
                                 at::cuda::getCurrentCUDAStream().stream());
 }
 
+// Q / R identification pass: tensors gt, imu, p, dp, contact, f [T][C][S]; q_diag [12][N], r_diag [10][N]; optional status [N]
+int kf_identify_noise(int64_t dtype, int64_t n_traj, int64_t n_steps, int64_t n_streams, int64_t stream_offset, int64_t alias_last,
+                      const std::map<std::string, double> &consts, const TensorMap &tensors) {
+    OptiKfIdentifyDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = (int32_t)dtype;
+    d.alias_last_measurement = (int32_t)alias_last;
+    d.n_traj = n_traj; d.n_steps = n_steps; d.n_streams = n_streams; d.stream_offset = stream_offset;
+    d.dt = consts.at("dt"); d.mass = consts.at("mass"); d.gravity = consts.at("gravity");
+    d.inertia[0] = consts.at("inertia0"); d.inertia[1] = consts.at("inertia1"); d.inertia[2] = consts.at("inertia2");
+    auto gt = tensors.find("gt");
+    TORCH_CHECK(gt != tensors.end() && gt->second.is_cuda(), "optistate_b200: 'gt' must be a CUDA tensor (there is no CPU path)");
+    const Checker ck{dtype == OPTI_KF_F64 ? at::kDouble : at::kFloat, gt->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    const int64_t N = n_traj, T = n_steps, S = n_streams;
+    d.gt = ck.get(tensors, "gt", T * 12 * S, true);
+    d.imu = ck.get(tensors, "imu", T * 6 * S, true);
+    d.p = ck.get(tensors, "p", T * 12 * S, true);
+    d.dp = ck.get(tensors, "dp", T * 12 * S, true);
+    d.contact = ck.get(tensors, "contact", T * 4 * S, true);
+    d.f = ck.get(tensors, "f", T * 12 * S, true);
+    d.q_diag = const_cast<void *>(ck.get(tensors, "q_diag", 12 * N, true));
+    d.r_diag = const_cast<void *>(ck.get(tensors, "r_diag", 10 * N, true));
+    auto it = tensors.find("stream_index");
+    if (it != tensors.end()) {
+        const at::Tensor &t = it->second;
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == N, "optistate_b200: bad 'stream_index'");
+        d.stream_index = t.data_ptr<int32_t>();
+    }
+    auto is = tensors.find("status");
+    if (is != tensors.end()) {
+        const at::Tensor &t = is->second;
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == N, "optistate_b200: bad 'status'");
+        d.status = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+    }
+    const size_t nb = optistate_kf_identify_scratch_bytes((int)dtype, N, T);
+    at::Tensor scratch = at::empty({(int64_t)nb}, gt->second.options().dtype(at::kByte));
+    d.scratch = scratch.data_ptr();
+    d.scratch_bytes = nb;
+    return optistate_kf_identify_noise(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
 std::pair<double, double> fma_peak(int64_t dtype, int64_t fma_per_thread) {
     double flops = 0, secs = 0;
     const int rc = optistate_fma_peak((int)dtype, fma_per_thread, &flops, &secs, at::cuda::getCurrentCUDAStream().stream());
@@ -278,6 +322,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_measure", &kf_measure);
     m.def("kf_resolve_algo", &kf_resolve_algo);
     m.def("fma_peak", &fma_peak);
+    m.def("kf_identify_noise", &kf_identify_noise);
     m.def("kf_features", &kf_features);
     m.def("kf_minmax", &kf_minmax);
     m.def("kf_windows", &kf_windows);

@@ -122,3 +122,20 @@ def test_gru_pipeline_restatement_shapes_and_reference_model_compatibility():
         x = torch.from_numpy(w)
         with torch.no_grad():
             assert torch.equal(ref_model(x), model(x))
+
+
+def test_identification_restatement_matches_reference_class_including_z_aliasing():
+    """oracle/identify_numpy.py vs the same loop driven through the unmodified reference class (build container only)."""
+    from oracle import identify_numpy, ref_shim
+    from optistate_b200.synth import make_stream
+
+    if not ref_shim.available():
+        pytest.skip("reference tree only exists in the build container")
+    s = make_stream(77, 120)
+    rng = np.random.default_rng(2)
+    gt = s["truth"] + 0.02 * rng.standard_normal(s["truth"].shape)
+    q_ref, r_ref = identify_numpy.identify_with_reference_class(gt, s["imu"], s["p"], s["dp"], s["contact"], s["f"])
+    q, r = identify_numpy.identify(gt, s["imu"], s["p"], s["dp"], s["contact"], s["f"], alias_last_measurement=True)
+    assert np.abs(q / q_ref - 1).max() < 1e-12 and np.abs(r / r_ref - 1).max() < 1e-12
+    q2, r2 = identify_numpy.identify(gt, s["imu"], s["p"], s["dp"], s["contact"], s["f"], alias_last_measurement=False)
+    assert np.allclose(q2, q) and not np.allclose(r2, r)  # the aliasing only changes R
