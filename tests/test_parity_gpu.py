@@ -302,3 +302,47 @@ def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
         assert parity.rel_err(packed.tensors[name].cpu().numpy(), scalar.tensors[name].cpu().numpy()) < 2e-5, name
     assert parity.rel_err(packed.summary.cpu().numpy(), scalar.summary.cpu().numpy()) < 1e-4
     assert torch.equal(packed.status, scalar.status) and int((packed.status & 4).sum()) // 4 == int((idx == 70).sum())
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full size (1,048,576 trajectories x 1,000 steps, FP32 Monte-Carlo noise sweep over 1,024 shared
+    streams), checked through size-independent properties: nominal members reproduce the nominal run (RMS deviation 0),
+    identical (stream, noise) pairs give identical summaries wherever they sit in the batch, no status flags, and a sample
+    of members agrees with the FP64 oracle within the stated FP32 tolerance."""
+    import bench
+
+    S, T, N = 1024, 1000, 1 << 20
+    st = make_streams(range(S), T)
+    dev = {k: torch.from_numpy(v).to("cuda", torch.float32) for k, v in st.items()}
+    q, r = bench.mc_noise(0, N, S)
+    q[:, -S:] = q[:, S:2 * S]  # the last pass over the streams repeats the noise of the second pass
+    r[:, -S:] = r[:, S:2 * S]
+    nominal = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], dtype=torch.float32, outputs=("x_steps",)).x_steps
+    res = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=q, R=r, n_traj=N, dtype=torch.float32,
+                   truth=dev["truth"], nominal=nominal, outputs=("summary",))
+    torch.cuda.synchronize()
+    sm = res.summary
+    assert int(res.status.max()) == 0 and bool(torch.isfinite(sm).all())
+    assert float(sm[36:48, :S].abs().max()) == 0.0          # nominal members: zero deviation from the nominal run
+    assert float(sm[36:48, S:].abs().max()) > 0.0
+    assert torch.equal(sm[:, -S:], sm[:, S:2 * S])          # same stream + same noise => same summary, anywhere in the batch
+    sample = np.array([0, 5, S + 17, 123457, N - 1])
+    ref = c_oracle.run(st, len(sample), Q=q[:, sample], R=r[:, sample], stream_index=(sample % S).astype(np.int32), want=("x_final", "P_final"))
+    x = sm[0:12, sample].cpu().numpy().astype(np.float64)
+    assert np.abs(x - ref["x_final"]).max() / np.abs(ref["x_final"]).max() < parity.FP32_TOL_X * 5
+    pd = sm[12:24, sample].cpu().numpy().astype(np.float64)
+    assert np.abs(pd - ref["P_final"][::13]).max() / np.abs(ref["P_final"]).max() < parity.FP32_TOL_P
+
+
+def test_sharded_entry_single_process_equals_plain_call():
+    from optistate_b200.distributed import kf_batch_sharded, shard_range
+
+    S, T, N = 64, 120, 512
+    st = make_streams(range(700, 700 + S), T)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in st.items()}
+    res, gathered = kf_batch_sharded(dev, N, dtype=torch.float64)
+    plain = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], n_traj=N, truth=dev["truth"], outputs=("summary",))
+    assert torch.equal(gathered, plain.summary) and shard_range(N, 1, 0) == (0, N)
+    # a shard that starts in the middle of the batch sees the same streams as the same members of the full batch
+    res2, _ = kf_batch_sharded(dev, N // 2, member_offset=N // 2, gather=False, dtype=torch.float64)
+    assert torch.equal(res2.summary, plain.summary[:, N // 2:])
