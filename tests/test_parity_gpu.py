@@ -304,7 +304,7 @@ def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
     assert torch.equal(packed.status, scalar.status) and int((packed.status & 4).sum()) // 4 == int((idx == 70).sum())
 
 
-def test_full_size_config3_properties():
+def test_full_size_config3_properties(monkeypatch):
     """BASELINE config 3 at full size (1,048,576 trajectories x 1,000 steps, FP32 Monte-Carlo noise sweep over 1,024 shared
     streams), checked through size-independent properties: nominal members reproduce the nominal run (RMS deviation 0),
     identical (stream, noise) pairs give identical summaries wherever they sit in the batch, no status flags, and a sample
@@ -317,6 +317,9 @@ def test_full_size_config3_properties():
     q, r = bench.mc_noise(0, N, S)
     q[:, -S:] = q[:, S:2 * S]  # the last pass over the streams repeats the noise of the second pass
     r[:, -S:] = r[:, S:2 * S]
+    # both passes on the packed two-trajectories-per-thread kernel: the one-trajectory FP32 kernel rounds sin/cos-derived
+    # entries differently in the last bit, and "deviation from the nominal member == 0" is a bitwise statement
+    monkeypatch.setenv("OPTISTATE_KF_PACKED", "1")
     nominal = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], dtype=torch.float32, outputs=("x_steps",)).x_steps
     res = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=q, R=r, n_traj=N, dtype=torch.float32,
                    truth=dev["truth"], nominal=nominal, outputs=("summary",))
