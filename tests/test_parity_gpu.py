@@ -349,3 +349,28 @@ def test_sharded_entry_single_process_equals_plain_call():
     # a shard that starts in the middle of the batch sees the same streams as the same members of the full batch
     res2, _ = kf_batch_sharded(dev, N // 2, member_offset=N // 2, gather=False, dtype=torch.float64)
     assert torch.equal(res2.summary, plain.summary[:, N // 2:])
+
+
+def test_host_pipeline_matches_plain_call_and_overlaps_slots():
+    """KfHostPipeline (pinned host buffers in, pinned host summaries out, double-buffered over three CUDA streams) returns
+    exactly what a plain kf_batch call returns, for more batches than slots and with different data per batch."""
+    from optistate_b200.pipeline import KfHostPipeline
+    from optistate_b200.synth import monte_carlo_noise
+
+    S, T, N = 64, 90, 256
+    st = make_streams(range(40, 40 + S), T)
+    pipe = KfHostPipeline(N, T, S, dtype=torch.float64, labels=("truth",), n_slots=2)
+    tickets, want = [], []
+    for b in range(5):
+        q, r = monte_carlo_noise(np.arange(N) + 1000 * b, np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT))
+        host = {k: torch.from_numpy(st[k] * (1.0 + 0.01 * b if k == "f" else 1.0)).pin_memory() for k in ("imu", "p", "dp", "contact", "f", "truth")}
+        host["Q"], host["R"] = torch.from_numpy(q).pin_memory(), torch.from_numpy(r).pin_memory()
+        ref = kf_batch(host["imu"], host["p"], host["dp"], host["contact"], host["f"], Q=q, R=r, n_traj=N, truth=host["truth"],
+                       outputs=("summary",), q_kind=2, r_kind=2).summary.cpu()
+        t = pipe.submit(host)
+        if len(tickets) >= 1:  # read the previous batch while this one is in flight
+            assert torch.equal(pipe.result(tickets[-1]).clone(), want[-1])
+        tickets.append(t)
+        want.append(ref)
+    pipe.drain()
+    assert torch.equal(pipe.result(tickets[-1]), want[-1])
