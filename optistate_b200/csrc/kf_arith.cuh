@@ -38,9 +38,33 @@ __device__ __forceinline__ double fnma_(double a, double b, double c) { return f
 __device__ __forceinline__ float fnma_(float a, float b, float c) { return fmaf(-a, b, c); }
 __device__ __forceinline__ F2 fnma_(F2 a, F2 b, F2 c) { return F2(__ffma2_rn((-a).v, b.v, c.v)); }
 
-__device__ __forceinline__ double rcp_(double a) { return 1.0 / a; }
-__device__ __forceinline__ float rcp_(float a) { return 1.0f / a; }
-__device__ __forceinline__ F2 rcp_(F2 a) { return F2(1.0f / a.v.x, 1.0f / a.v.y); }
+// Reciprocal of a pivot (positive, normal; anything else is flagged NOT_PD by the caller): hardware seed (MUFU.RCP64H /
+// MUFU.RCP) refined by Newton steps, straight-line.  The IEEE division `1.0 / a` costs the same FMAs plus a
+// special-case branch with a slow-path call, and that branch splits the time loop into basic blocks across which the
+// scheduler cannot overlap the reciprocal chain with the rank-1 FMAs.  Relative error <= 2 ulp.
+__device__ __forceinline__ double rcp_(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));  // ~20 good bits
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);  // ~40 bits
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);  // ~80 bits -> rounding-limited
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);  // one more step removes the residual of the seed's worst case
+}
+__device__ __forceinline__ float rcp_(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    const float e = fmaf(-a, r, 1.0f);
+    return fmaf(r, e, r);
+}
+__device__ __forceinline__ F2 rcp_(F2 a) {
+    F2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.v.x) : "f"(a.v.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.v.y) : "f"(a.v.y));
+    const F2 e = F2(__ffma2_rn((-a).v, r.v, make_float2(1.0f, 1.0f)));
+    return F2(__ffma2_rn(r.v, e.v, r.v));
+}
 __device__ __forceinline__ double div_(double a, double b) { return a / b; }
 __device__ __forceinline__ float div_(float a, float b) { return a / b; }
 __device__ __forceinline__ F2 div_(F2 a, F2 b) { return F2(a.v.x / b.v.x, a.v.y / b.v.y); }
