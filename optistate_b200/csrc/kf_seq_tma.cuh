@@ -215,7 +215,7 @@ __device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm,
 }
 
 template <typename Real, bool kSummary>
-__global__ void __launch_bounds__(TMA_THREADS) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
+__global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) ? 3 : 2) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
     using AccT = typename Acc<Real>::type;
