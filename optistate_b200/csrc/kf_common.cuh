@@ -34,12 +34,56 @@ struct Params {
     const uint32_t *stream_status;  // [S] per-stream flags of the measurement pre-pass, OR-ed into status
 };
 
+// sin and cos of an attitude angle, straight-line (no slow-path branch, so the trigonometry of the NEXT step can be
+// scheduled underneath the rank-1 FMAs of the current one): Cody-Waite reduction by pi/2 with fused steps, then the
+// fdlibm (FP64) / Cephes (FP32) kernel polynomials on [-pi/4, pi/4] and a branch-free quadrant fix-up.  Error <= ~1 ulp for
+// |angle| < ~1e6 rad (FP64) / ~8e3 rad (FP32); sin(0) = 0, cos(0) = 1 and sin(nearest(pi/2)) = 1 exactly, which is what
+// the trunc(R^T) semantics of the mean model depend on.
 template <typename Real> __device__ __forceinline__ void sincos_full(Real a, Real &s, Real &c);
-template <> __device__ __forceinline__ void sincos_full<double>(double a, double &s, double &c) { sincos(a, &s, &c); }
-template <> __device__ __forceinline__ void sincos_full<float>(float a, float &s, float &c) { sincosf(a, &s, &c); }
+template <> __device__ __forceinline__ void sincos_full<double>(double x, double &s, double &c) {
+    const double q = rint(x * 6.36619772367581382433e-01);
+    double r = fma(-q, 1.57079632673412561417e+00, x);
+    r = fma(-q, 6.07710050630396597660e-11, r);
+    r = fma(-q, 2.02226624871116645580e-21, r);
+    r = fma(-q, 8.47842766036889956997e-32, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = 1.0 - fma(0.5, z, -(z * (z * pc)));
+    const int n = __double2int_rn(q);
+    const double s0 = (n & 1) ? cr : sr, c0 = (n & 1) ? sr : cr;
+    s = (n & 2) ? -s0 : s0;
+    c = ((n + 1) & 2) ? -c0 : c0;
+}
+template <> __device__ __forceinline__ void sincos_full<float>(float x, float &s, float &c) {
+    const float q = rintf(x * 0.636619772367581343f);
+    float r = fmaf(-q, 1.5703125f, x);
+    r = fmaf(-q, 4.837512969970703125e-4f, r);
+    r = fmaf(-q, 7.54978995489188216e-8f, r);
+    const float z = r * r;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(z, ps, -1.6666654611e-1f);
+    const float sr = fmaf(z * r, ps, r);
+    float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(z, pc, 4.166664568298827e-2f);
+    const float cr = 1.0f - fmaf(0.5f, z, -(z * (z * pc)));
+    const int n = __float2int_rn(q);
+    const float s0 = (n & 1) ? cr : sr, c0 = (n & 1) ? sr : cr;
+    s = (n & 2) ? -s0 : s0;
+    c = ((n + 1) & 2) ? -c0 : c0;
+}
 template <> __device__ __forceinline__ void sincos_full<F2>(F2 a, F2 &s, F2 &c) {
-    sincosf(a.v.x, &s.v.x, &c.v.x);
-    sincosf(a.v.y, &s.v.y, &c.v.y);
+    sincos_full<float>(a.v.x, s.v.x, c.v.x);
+    sincos_full<float>(a.v.y, s.v.y, c.v.y);
 }
 
 // products/sums that must not be contracted into FMAs: the entries of R decide trunc(R^T) below
