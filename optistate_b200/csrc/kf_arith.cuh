@@ -115,6 +115,10 @@ __device__ __forceinline__ F2 to_acc(F2 v) { return v; }
 __device__ __forceinline__ double err_sq(double x, double lab) { const double e = x - lab; return e * e; }
 __device__ __forceinline__ double err_sq(float x, float lab) { const double e = (double)x - (double)lab; return e * e; }
 __device__ __forceinline__ F2 err_sq(F2 x, F2 lab) { const F2 e = x - lab; return e * e; }
+// acc + (x - lab)^2, fused
+__device__ __forceinline__ double err_acc(double acc, double x, double lab) { const double e = x - lab; return fma(e, e, acc); }
+__device__ __forceinline__ double err_acc(double acc, float x, float lab) { const double e = (double)x - (double)lab; return fma(e, e, acc); }
+__device__ __forceinline__ F2 err_acc(F2 acc, F2 x, F2 lab) { const F2 e = x - lab; return fma_(e, e, acc); }
 __device__ __forceinline__ double rms_out(double acc, double inv_t, double) { return sqrt(acc * inv_t); }
 __device__ __forceinline__ float rms_out(double acc, double inv_t, float) { return (float)sqrt(acc * inv_t); }
 __device__ __forceinline__ F2 rms_out(F2 acc, double inv_t, F2) { return F2(sqrtf(acc.v.x * (float)inv_t), sqrtf(acc.v.y * (float)inv_t)); }

@@ -402,15 +402,28 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             if (n_lab) {
                 mbar_wait(&bars[2], par);
                 const Real *lab = g2w + lane;
-                if (prm.truth) {
+                // labels and running sums are fetched six at a time BEFORE they are used, so the shared-memory latency of
+                // one batch overlaps the arithmetic of the previous one instead of stalling every single update
+                auto accumulate = [&](int acc0, int lab0) {
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) acc_add(c, err_sq(x[c], lab[c * 32]));
-                }
-                if (prm.nominal) {
-                    const int base = prm.truth ? 12 : 0;
+                    for (int c0 = 0; c0 < NX; c0 += 6) {
+                        Real lv[6];
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) acc_add(12 + c, err_sq(x[c], lab[(base + c) * 32]));
-                }
+                        for (int c = 0; c < 6; ++c) lv[c] = lab[(lab0 + c0 + c) * 32];
+                        if constexpr (kAccSmem) {
+                            AccT av[6];
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) av[c] = acc_s[(acc0 + c0 + c) * nt];
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) acc_s[(acc0 + c0 + c) * nt] = err_acc(av[c], x[c0 + c], lv[c]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) acc_r[acc0 + c0 + c] = err_acc(acc_r[acc0 + c0 + c], x[c0 + c], lv[c]);
+                        }
+                    }
+                };
+                if (prm.truth) accumulate(0, 0);
+                if (prm.nominal) accumulate(12, prm.truth ? 12 : 0);
                 __syncwarp();
                 if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], lane);
             }
