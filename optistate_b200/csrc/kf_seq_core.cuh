@@ -1,0 +1,207 @@
+// Arithmetic core of the SEQUENTIAL path, shared by the TMA-fed kernel (kf_seq_tma.cuh) and the direct-load kernel
+// (kf_seq.cuh); generic over Real = double | float | F2 (kf_arith.cuh).
+//
+//   * P is a packed symmetric matrix (78 scalars) that lives in registers for the whole time loop; x (12) too.
+//   * The covariance transition F_d P F_d^T + Q (kalman_filter.py:125-135) is evaluated block-wise on the packed form in
+//     the reference's W = F_d P, P' = W F_d^T order, skipping the structural zeros of F_d (168 FMAs).
+//   * The update (kalman_filter.py:164-174) folds the 10 measurements in one at a time.  For diagonal R this is the same
+//     Schur complement the reference evaluates jointly as P - (P H^T) S^-1 (H P): eliminating the block [[S, HP],[PH^T, P]]
+//     at once or one scalar pivot after the other gives the same result (also for a non-symmetric P, because with a
+//     diagonal R the pivot block of the augmented matrix is P[sel,sel] + R at every stage).  No 10x10 factorisation, no
+//     square roots, no gain matrix: per measurement 1 reciprocal + 101 FMAs; row / column k of the result is the old
+//     column times r/s, so the old column stays in place until the end and is never copied.
+//     K_gain = sum_i K[i][i] follows from the identity K = P'[:, sel] R^-1, NIS from sum_k y_k^2 / s_k.
+//   * Independent trajectories => no shuffles, no shared-memory traffic in the recursion, no redundant work.
+#pragma once
+
+#include "kf_common.cuh"
+
+namespace okf {
+
+__host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+constexpr int NP = 78;
+
+// P <- F_d P F_d^T + diag(q), F_d = I + dt N, N[a,c] = R^T, N[b,d] = I   (blocks a=0..2 b=3..5 c=6..8 d=9..11)
+// Written with explicit fma_ so that double, float and the packed F2 type run the same operation sequence.
+template <typename Real, typename Scalar>
+__device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9], Scalar dt_s, const Real *q, int qs) {
+    constexpr int a = 0, b = 3, c = 6, d = 9;
+    const Real dt = Real(dt_s);
+    Real A[9];  // A = dt R^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) A[3 * i + k] = dt * R[3 * k + i];
+        // W rows that feed P'[a,a], P'[b,a], P'[b,b] use the OLD c- and d-rows: do them first.
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            Real s = P[tri(a + i, a + j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma_(A[3 * i + k], P[tri(c + k, a + j)], s);
+            P[tri(a + i, a + j)] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) P[tri(b + i, a + j)] = fma_(dt, P[tri(d + i, a + j)], P[tri(b + i, a + j)]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + i, b + j)], P[tri(b + i, b + j)]);
+        // P'[c,a] = P[c,a] + P[c,c] A^T ; P'[d,a] = P[d,a] + P[d,c] A^T ; P'[c,b] = P[c,b] + dt P[c,d] ; P'[d,b] = P[d,b] + dt P[d,d]
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Real s = P[tri(c + i, a + j)], u = P[tri(d + i, a + j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                s = fma_(P[tri(c + i, c + k)], A[3 * j + k], s);
+                u = fma_(P[tri(d + i, c + k)], A[3 * j + k], u);
+            }
+            P[tri(c + i, a + j)] = s;
+            P[tri(d + i, a + j)] = u;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            P[tri(c + i, b + j)] = fma_(dt, P[tri(d + j, c + i)], P[tri(c + i, b + j)]);
+            P[tri(d + i, b + j)] = fma_(dt, P[tri(d + i, d + j)], P[tri(d + i, b + j)]);
+        }
+        // second factor: + W[a,c] A^T, + W[b,c] A^T, + dt W[b,d], with W[.,c] = P'[c,.]^T and W[b,d] = P'[d,b]^T
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            Real s = P[tri(a + i, a + j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, a + i)], A[3 * j + k], s);
+            P[tri(a + i, a + j)] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Real s = P[tri(b + i, a + j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, b + i)], A[3 * j + k], s);
+            P[tri(b + i, a + j)] = s;
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + j, b + i)], P[tri(b + i, b + j)]);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) P[tri(i, i)] += q[i * qs];
+}
+
+// Measurement J folded in with the reciprocal of its pivot already available (`inv` = 1 / (P_kk + r_J)).  The entry
+// that becomes the NEXT pivot is updated first and its reciprocal started at once, so that chain (MUFU + Newton
+// steps) runs underneath the 65 remaining independent FMAs of this rank-1 update.  `mid` runs after the state update.
+template <int J, typename Real, int L, typename Mid>
+__device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Real zj, Real rj, Real r_next, Real inv, Real &inv_next,
+                                               Real &nis, uint32_t (&status)[L], Mid mid) {
+    constexpr int k = sel(J);
+    constexpr int kn = (J + 1 < NZ) ? sel(J + 1) : -1;
+    if constexpr (kn >= 0) {
+        const Real wn = P[tri(kn, k)] * inv;
+        const Real pnn = fnma_(wn, P[tri(kn, k)], P[tri(kn, kn)]);
+        P[tri(kn, kn)] = pnn;
+        const Real s = pnn + r_next;
+        note_bad_pivot(s, status, OPTI_KF_ST_NOT_PD);
+        inv_next = rcp_(s);
+    }
+    const Real y = zj - x[k];
+    const Real g = inv * y;
+    nis = fma_(y, g, nis);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = fma_(P[tri(i, k)], g, x[i]);
+    mid();
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        if (i == k) continue;
+        const Real w = P[tri(i, k)] * inv;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            if (j == k || (i == kn && j == kn)) continue;
+            P[tri(i, j)] = fnma_(w, P[tri(j, k)], P[tri(i, j)]);
+        }
+    }
+    const Real cfac = rj * inv;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
+}
+
+// cheap test whether trunc(R^T) can have a non-zero entry in any lane (then the exact decision is taken per lane)
+template <typename Real>
+__device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
+    using S = typename Lanes<Real>::scalar;
+    S m = S(0);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m = max_(m, absmax_lanes(R[k]));
+    return m >= (sizeof(S) == 8 ? S(1) : S(1.0f - 9.5367431640625e-7f));
+}
+
+// Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
+// Feet and forces are read leg by leg through `pin` / `fin` (channel stride STRIDE: 32 for a warp's shared-memory tile,
+// 1 for a per-thread array) so that at most one leg is live in registers; `pw_out` (optional) receives the feet rotated
+// into the world frame (the reference's in-place mutation of p, force_controller.py:274-277).
+template <int STRIDE, typename Real, typename Scalar>
+__device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm, Real (&x)[NX], const Real *pin, const Real *fin,
+                                                      const Real (&R)[9], bool any_trunc, Scalar *pw_out, long long pw_idx, long long pw_stride) {
+    constexpr int L = Lanes<Real>::n;
+    Real tau[3] = {Real(0), Real(0), Real(0)}, fs[3] = {Real(0), Real(0), Real(0)};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        const Real a = pin[(3 * l) * STRIDE], b = pin[(3 * l + 1) * STRIDE], c = pin[(3 * l + 2) * STRIDE];
+        const Real pw0 = fma_(R[2], c, fma_(R[1], b, R[0] * a));
+        const Real pw1 = fma_(R[5], c, fma_(R[4], b, R[3] * a));
+        const Real pw2 = fma_(R[8], c, fma_(R[7], b, R[6] * a));
+        if (pw_out) {
+            st_traj(pw_out, pw_idx + (3 * l) * pw_stride, pw0);
+            st_traj(pw_out, pw_idx + (3 * l + 1) * pw_stride, pw1);
+            st_traj(pw_out, pw_idx + (3 * l + 2) * pw_stride, pw2);
+        }
+        const Real f0 = fin[(3 * l) * STRIDE], f1 = fin[(3 * l + 1) * STRIDE], f2 = fin[(3 * l + 2) * STRIDE];
+        tau[0] += fnma_(pw2, f1, pw1 * f2);
+        tau[1] += fnma_(pw0, f2, pw2 * f0);
+        tau[2] += fnma_(pw1, f0, pw0 * f1);
+        fs[0] += f0; fs[1] += f1; fs[2] += f2;
+    }
+    Real u[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[k] = fma_(R[6 + k], tau[2], fma_(R[3 + k], tau[1], R[k] * tau[0])) * Real(prm.inv_inertia[k]);
+    Real dth[3] = {Real(0), Real(0), Real(0)};
+    if (any_trunc) {  // rare: an entry of R is exactly +-1 (axis-aligned attitude); exact per-lane decision in trunc_rt
+#pragma unroll
+        for (int ln = 0; ln < L; ++ln) {
+            Scalar Rs[9], Ts[9], ang[3];
+            bool any;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rs[k] = lane_get(R[k], ln);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ang[k] = lane_get(x[k], ln);
+            trunc_rt(Rs, ang, Ts, any);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                lane_set(dth[i], ln, prm.dt * (Ts[3 * i] * lane_get(x[6], ln) + Ts[3 * i + 1] * lane_get(x[7], ln) + Ts[3 * i + 2] * lane_get(x[8], ln)));
+        }
+    }
+    const Real dt = Real(prm.dt);
+    Real xn[NX];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        xn[i] = x[i] + dth[i];
+        xn[3 + i] = fma_(dt, x[9 + i], x[3 + i]);
+        xn[6 + i] = fma_(dt, fma_(R[3 * i + 2], u[2], fma_(R[3 * i + 1], u[1], R[3 * i] * u[0])), x[6 + i]);
+        xn[9 + i] = fma_(Real(prm.dt_over_m), fs[i], x[9 + i]);
+    }
+    xn[11] += Real(prm.dt_g);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+}
+
+}  // namespace okf

@@ -1,4 +1,4 @@
-// Throughput kernel, streamed variant: same arithmetic as kf_seq.cuh (one thread per trajectory, packed symmetric
+// Throughput kernel, streamed variant: the arithmetic of kf_seq_core.cuh (one thread per trajectory, packed symmetric
 // P and x in registers, sequential scalar updates) with the per-step inputs delivered by the TMA engine.
 //
 //   * 32 consecutive trajectories (one warp) read 32 consecutive base streams, so the inputs of one step are
@@ -25,7 +25,7 @@
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
-#include "kf_seq.cuh"
+#include "kf_seq_core.cuh"
 
 namespace okf {
 
@@ -107,111 +107,6 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
         tma_tile_g2s(g2w, &m.lab0, s_warp, (int)(t * 12), bar);
         if (n_lab > 1) tma_tile_g2s(g2w + 12 * 32, &m.lab1, s_warp, (int)(t * 12), bar);
     }
-}
-
-// Measurement J folded in with the reciprocal of its pivot already available (`inv` = 1 / (P_kk + r_J)).  The entry
-// that becomes the NEXT pivot is updated first and its reciprocal started at once, so that chain (MUFU + Newton
-// steps) runs underneath the 65 remaining independent FMAs of this rank-1 update.  `mid` runs after the state update.
-template <int J, typename Real, int L, typename Mid>
-__device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Real zj, Real rj, Real r_next, Real inv, Real &inv_next,
-                                               Real &nis, uint32_t (&status)[L], Mid mid) {
-    constexpr int k = sel(J);
-    constexpr int kn = (J + 1 < NZ) ? sel(J + 1) : -1;
-    if constexpr (kn >= 0) {
-        const Real wn = P[tri(kn, k)] * inv;
-        const Real pnn = fnma_(wn, P[tri(kn, k)], P[tri(kn, kn)]);
-        P[tri(kn, kn)] = pnn;
-        const Real s = pnn + r_next;
-        note_bad_pivot(s, status, OPTI_KF_ST_NOT_PD);
-        inv_next = rcp_(s);
-    }
-    const Real y = zj - x[k];
-    const Real g = inv * y;
-    nis = fma_(y, g, nis);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = fma_(P[tri(i, k)], g, x[i]);
-    mid();
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        if (i == k) continue;
-        const Real w = P[tri(i, k)] * inv;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            if (j == k || (i == kn && j == kn)) continue;
-            P[tri(i, j)] = fnma_(w, P[tri(j, k)], P[tri(i, j)]);
-        }
-    }
-    const Real cfac = rj * inv;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
-}
-
-// cheap test whether trunc(R^T) can have a non-zero entry in any lane (then the exact decision is taken per lane)
-template <typename Real>
-__device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
-    using S = typename Lanes<Real>::scalar;
-    S m = S(0);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) m = max_(m, absmax_lanes(R[k]));
-    return m >= (sizeof(S) == 8 ? S(1) : S(1.0f - 9.5367431640625e-7f));
-}
-
-// Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).
-// Feet and forces are read leg by leg straight from the warp's shared-memory tile (`pin`, `fin`: channel stride 32)
-// so that at most one leg is live in registers; `pw_out` (optional) receives the feet rotated into the world frame.
-template <typename Real, typename Scalar>
-__device__ __forceinline__ void propagate_mean_with_R(const Params<Scalar> &prm, Real (&x)[NX], const Real *pin, const Real *fin,
-                                                      const Real (&R)[9], bool any_trunc, Scalar *pw_out, long long pw_idx, long long pw_stride) {
-    constexpr int L = Lanes<Real>::n;
-    Real tau[3] = {Real(0), Real(0), Real(0)}, fs[3] = {Real(0), Real(0), Real(0)};
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const Real a = pin[(3 * l) * 32], b = pin[(3 * l + 1) * 32], c = pin[(3 * l + 2) * 32];
-        const Real pw0 = fma_(R[2], c, fma_(R[1], b, R[0] * a));
-        const Real pw1 = fma_(R[5], c, fma_(R[4], b, R[3] * a));
-        const Real pw2 = fma_(R[8], c, fma_(R[7], b, R[6] * a));
-        if (pw_out) {
-            st_traj(pw_out, pw_idx + (3 * l) * pw_stride, pw0);
-            st_traj(pw_out, pw_idx + (3 * l + 1) * pw_stride, pw1);
-            st_traj(pw_out, pw_idx + (3 * l + 2) * pw_stride, pw2);
-        }
-        const Real f0 = fin[(3 * l) * 32], f1 = fin[(3 * l + 1) * 32], f2 = fin[(3 * l + 2) * 32];
-        tau[0] += fnma_(pw2, f1, pw1 * f2);
-        tau[1] += fnma_(pw0, f2, pw2 * f0);
-        tau[2] += fnma_(pw1, f0, pw0 * f1);
-        fs[0] += f0; fs[1] += f1; fs[2] += f2;
-    }
-    Real u[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) u[k] = fma_(R[6 + k], tau[2], fma_(R[3 + k], tau[1], R[k] * tau[0])) * Real(prm.inv_inertia[k]);
-    Real dth[3] = {Real(0), Real(0), Real(0)};
-    if (any_trunc) {  // rare: an entry of R is exactly +-1 (axis-aligned attitude); exact per-lane decision in trunc_rt
-#pragma unroll
-        for (int ln = 0; ln < L; ++ln) {
-            Scalar Rs[9], Ts[9], ang[3];
-            bool any;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) Rs[k] = lane_get(R[k], ln);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ang[k] = lane_get(x[k], ln);
-            trunc_rt(Rs, ang, Ts, any);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                lane_set(dth[i], ln, prm.dt * (Ts[3 * i] * lane_get(x[6], ln) + Ts[3 * i + 1] * lane_get(x[7], ln) + Ts[3 * i + 2] * lane_get(x[8], ln)));
-        }
-    }
-    const Real dt = Real(prm.dt);
-    Real xn[NX];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        xn[i] = x[i] + dth[i];
-        xn[3 + i] = fma_(dt, x[9 + i], x[3 + i]);
-        xn[6 + i] = fma_(dt, fma_(R[3 * i + 2], u[2], fma_(R[3 * i + 1], u[1], R[3 * i] * u[0])), x[6 + i]);
-        xn[9 + i] = fma_(Real(prm.dt_over_m), fs[i], x[9 + i]);
-    }
-    xn[11] += Real(prm.dt_g);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = xn[i];
 }
 
 template <typename Real, bool kSummary>
@@ -324,7 +219,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 
         // ---- G0: feet and forces -> mean model --------------------------------------------------------------
         mbar_wait(&bars[0], par);
-        propagate_mean_with_R(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc, active ? prm.p_world_steps : nullptr,
+        propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc, active ? prm.p_world_steps : nullptr,
                               (t * 12) * N + i, N);
         __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
         if (more) issue_g0(maps, t + 1, s_warp, g0w, &bars[0], lane);
