@@ -50,6 +50,27 @@ __device__ __forceinline__ Real mat_at(const Real *M, int kind, int n, int a, in
     }
 }
 
+// lane q's three entries 3q..3q+2 of a replicated 12-vector, without dynamic register indexing
+template <typename Real>
+__device__ __forceinline__ void own3(const Real (&v)[NX], int q, Real (&o)[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) o[a] = q == 0 ? v[a] : q == 1 ? v[3 + a] : q == 2 ? v[6 + a] : v[9 + a];
+}
+
+// noise matrices without per-element switches: element e of a dense matrix / entry a of a diagonal lives at
+// base[e * stride + offset] with (stride, offset) = (1, 0) for a shared array and (N, i) for a per-trajectory one
+template <typename Real>
+struct NoiseView {
+    const Real *base;
+    long long stride, offset;
+    bool dense;
+    __device__ __forceinline__ NoiseView(const Real *m, int kind, long long N, long long i)
+        : base(m), stride((kind == OPTI_KF_MAT_DIAG_PER || kind == OPTI_KF_MAT_DENSE_PER) ? N : 1),
+          offset((kind == OPTI_KF_MAT_DIAG_PER || kind == OPTI_KF_MAT_DENSE_PER) ? i : 0),
+          dense(kind == OPTI_KF_MAT_DENSE || kind == OPTI_KF_MAT_DENSE_PER) {}
+    __device__ __forceinline__ Real at(int e) const { return __ldg(base + e * stride + offset); }
+};
+
 // in-place inverse of the 10x10 matrix at lm_ (element (i,j) at lm_[(i*10+j)*JC_TRAJ]) by Gauss-Jordan with partial pivoting
 template <typename Real>
 __device__ __noinline__ bool invert10_inplace(Real *lm_) {
@@ -107,18 +128,15 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 #define LM(e) lm_[(e) * JC_TRAJ]
 #define VC(e) vc_[(e) * JC_TRAJ]
 
+    const NoiseView<Real> Qv(prm.Q, prm.q_kind, N, i), Rv(prm.R, prm.r_kind, N, i);
     Real Pr[3][NX], Kr[3][NZ], x[NX];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int b = 0; b < NX; ++b) {
             const int row = r0 + a;
-            Real v;
-            switch (prm.p0_kind) {
-                case OPTI_KF_MAT_NONE: v = mat_at(prm.Q, prm.q_kind, NX, row, b, N, i); break;
-                default: v = mat_at(prm.P0, prm.p0_kind, NX, row, b, N, i); break;
-            }
-            Pr[a][b] = v;
+            Pr[a][b] = prm.p0_kind == OPTI_KF_MAT_NONE ? mat_at(prm.Q, prm.q_kind, NX, row, b, N, i)
+                                                        : mat_at(prm.P0, prm.p0_kind, NX, row, b, N, i);
         }
 #pragma unroll
         for (int j = 0; j < NZ; ++j) Kr[a][j] = Real(0);
@@ -128,12 +146,15 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 
     uint32_t status = 0;
     Real ptrace = Real(0), kgain = Real(0), ymax = Real(0);
-    {
+    auto own_trace = [&]() {  // sum of this lane's diagonal entries P[3q+a][3q+a], compile-time register indices only
         Real d = Real(0);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) d += Pr[a][r0 + a];
-        ptrace = quad_sum(d);
-    }
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < NX; ++c) d += (c == r0 + a) ? Pr[a][c] : Real(0);
+        return d;
+    };
+    ptrace = quad_sum(own_trace());
     double acc_truth[3] = {0.0, 0.0, 0.0}, acc_nom[3] = {0.0, 0.0, 0.0}, acc_nis = 0.0;
 
     for (long long t = 0; t < prm.T; ++t) {
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                         Real acc = Real(0);
 #pragma unroll
                         for (int m = 0; m < NX; ++m) acc += W[a][m] * fd(c, m);
-                        Pr[a][c] = acc + mat_at(prm.Q, prm.q_kind, NX, r0 + a, c, N, i);
+                        Pr[a][c] = acc + (Qv.dense ? Qv.at((r0 + a) * NX + c) : (c == r0 + a ? Qv.at(r0 + a) : Real(0)));
                     }
                 propagate_mean(prm, x, pf, ff, Rm);
             } else {
@@ -234,26 +255,28 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                         Pr[a][j] += prm.dt * (w6 * Rm[j] + w7 * Rm[3 + j] + w8 * Rm[6 + j]);
                         Pr[a][3 + j] += prm.dt * Pr[a][9 + j];
                     }
+                    if (Qv.dense) {
 #pragma unroll
-                    for (int c = 0; c < NX; ++c) {
-                        if (prm.q_kind == OPTI_KF_MAT_DENSE || prm.q_kind == OPTI_KF_MAT_DENSE_PER || c == r0 + a)
-                            Pr[a][c] += mat_at(prm.Q, prm.q_kind, NX, r0 + a, c, N, i);
+                        for (int c = 0; c < NX; ++c) Pr[a][c] += Qv.at((r0 + a) * NX + c);
+                    } else {
+                        const Real qd = Qv.at(r0 + a);
+#pragma unroll
+                        for (int c = 0; c < NX; ++c) Pr[a][c] += (c == r0 + a) ? qd : Real(0);
                     }
                 }
             }
-            {
-                Real d = Real(0);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) d += Pr[a][r0 + a];
-                ptrace = quad_sum(d);
-            }
+            ptrace = quad_sum(own_trace());
             if (active && prm.x_model_steps) {
+                Real xo[3];
+                own3(x, q, xo);
 #pragma unroll
-                for (int a = 0; a < 3; ++a) st_stream(prm.x_model_steps + (t * NX + r0 + a) * N + i, x[r0 + a]);
+                for (int a = 0; a < 3; ++a) st_stream(prm.x_model_steps + (t * NX + r0 + a) * N + i, xo[a]);
             }
             if (active && prm.p_world_steps) {  // lane q stores foot q
+                Real po[3];
+                own3(pf, q, po);
 #pragma unroll
-                for (int a = 0; a < 3; ++a) st_stream(prm.p_world_steps + (t * 12 + r0 + a) * N + i, pf[r0 + a]);
+                for (int a = 0; a < 3; ++a) st_stream(prm.p_world_steps + (t * 12 + r0 + a) * N + i, po[a]);
             }
         }
 
@@ -266,17 +289,30 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 #pragma unroll
                 for (int c = 0; c < NX; ++c) PF((r0 + a) * NX + c) = Pr[a][c];
             __syncwarp();
-            for (int e = q; e < NZ * NZ; e += 4) {
-                const int a = e / NZ, b = e % NZ;
-                LM(e) = PF(sel(a) * NX + sel(b)) + mat_at(prm.R, prm.r_kind, NZ, a, b, N, i);
+            // S = P[sel,sel] + R: lane q forms rows q, q+4, q+8
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int a = q + 4 * rr;
+                if (a < NZ) {
+                    const int sa = a < 3 ? a : a + 2;
+#pragma unroll
+                    for (int b = 0; b < NZ; ++b) {
+                        const Real rn = Rv.dense ? Rv.at(a * NZ + b) : (a == b ? Rv.at(a) : Real(0));
+                        LM(a * NZ + b) = PF(sa * NX + sel(b)) + rn;
+                    }
+                }
             }
             __syncwarp();
             uint32_t asym = 0;
-            for (int e = q; e < NZ * NZ; e += 4) {
-                const int a = e / NZ, b = e % NZ;
-                if (a > b) {
-                    const Real d = fabs(LM(a * NZ + b) - LM(b * NZ + a));
-                    if (d > Real(sizeof(Real) == 8 ? 1e-12 : 1e-5) * sqrt(fabs(LM(a * NZ + a) * LM(b * NZ + b)))) asym = 1;
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int a = q + 4 * rr;
+                if (a < NZ) {
+#pragma unroll
+                    for (int b = 0; b < NZ; ++b) {
+                        const Real d = fabs(LM(a * NZ + b) - LM(b * NZ + a));
+                        if (d > Real(sizeof(Real) == 8 ? 5e-13 : 5e-6) * (fabs(LM(a * NZ + a)) + fabs(LM(b * NZ + b)))) asym = 1;
+                    }
                 }
             }
             asym = quad_or(asym);
@@ -286,20 +322,24 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 
             if (!asym) {
                 // cooperative Cholesky, in place in the lower triangle of LM; dinv[j] = 1 / L[j][j] in VC
-#pragma unroll 1
+#pragma unroll
                 for (int j = 0; j < NZ; ++j) {
                     Real d = LM(j * NZ + j);
+#pragma unroll
                     for (int k = 0; k < j; ++k) d -= LM(j * NZ + k) * LM(j * NZ + k);
                     if (!(d > Real(0)) || !(d < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
-                    const Real ljj = sqrt(d);
-                    const Real dinv = Real(1) / ljj;
-                    for (int r = j + 1 + q; r < NZ; r += 4) {
-                        Real v = LM(r * NZ + j);
-                        for (int k = 0; k < j; ++k) v -= LM(r * NZ + k) * LM(j * NZ + k);
-                        LM(r * NZ + j) = v * dinv;
+                    const Real dinv = rsqrt(d);  // 1 / L[j][j]
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) {
+                        const int r = j + 1 + q + 4 * rr;
+                        if (r < NZ) {
+                            Real v = LM(r * NZ + j);
+#pragma unroll
+                            for (int k = 0; k < j; ++k) v -= LM(r * NZ + k) * LM(j * NZ + k);
+                            LM(r * NZ + j) = v * dinv;
+                        }
                     }
-                    __syncwarp();  // every lane has read the old diagonal entry before it is overwritten
-                    if (q == 0) { LM(j * NZ + j) = ljj; VC(j) = dinv; }
+                    if (q == 0) VC(j) = dinv;
                     __syncwarp();
                 }
                 // NIS = |L^-1 y|^2 (replicated) and the three K rows of this lane: L u = P[i,sel]^T, then L^T k = u
@@ -359,12 +399,13 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
             // x <- x + K y: three entries per lane, then an all-gather over the quad
             {
                 Real xo[3];
+                own3(x, q, xo);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     Real v = Real(0);
 #pragma unroll
                     for (int j = 0; j < NZ; ++j) v += Kr[a][j] * y[j];
-                    xo[a] = x[r0 + a] + v;
+                    xo[a] += v;
                 }
 #pragma unroll
                 for (int src = 0; src < 4; ++src)
@@ -379,24 +420,25 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                     const Real ps = PF(sel(j) * NX + c);
                     Pr[0][c] -= Kr[0][j] * ps; Pr[1][c] -= Kr[1][j] * ps; Pr[2][c] -= Kr[2][j] * ps;
                 }
-            Real d = Real(0), g = Real(0);
+            Real g = Real(0);  // np.trace of the 12x10 gain: K[j][j], j < 10
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                d += Pr[a][r0 + a];
-                if (r0 + a < NZ) g += Kr[a][r0 + a];  // np.trace of the 12x10 gain
-            }
-            ptrace = quad_sum(d);
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int j = 0; j < NZ; ++j) g += (j == r0 + a) ? Kr[a][j] : Real(0);
+            ptrace = quad_sum(own_trace());
             kgain = quad_sum(g);
             ymax = fmax(ymax, nis);
         }
+        Real xq[3];
+        own3(x, q, xq);
 #pragma unroll
         for (int a = 0; a < 3; ++a)
-            if (!isfinite(x[r0 + a])) status |= OPTI_KF_ST_NONFINITE;
+            if (!isfinite(xq[a])) status |= OPTI_KF_ST_NONFINITE;
 
         if (active) {
             if (prm.x_steps) {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) st_stream(prm.x_steps + (t * NX + r0 + a) * N + i, x[r0 + a]);
+                for (int a = 0; a < 3; ++a) st_stream(prm.x_steps + (t * NX + r0 + a) * N + i, xq[a]);
             }
             if (q == 0) {
                 if (prm.p_trace_steps) st_stream(prm.p_trace_steps + t * N + i, ptrace);
@@ -416,11 +458,11 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 if (prm.truth) {
-                    const double e = (double)x[r0 + a] - (double)ld_stream(prm.truth + (t * NX + r0 + a) * S + s);
+                    const double e = (double)xq[a] - (double)ld_stream(prm.truth + (t * NX + r0 + a) * S + s);
                     acc_truth[a] += e * e;
                 }
                 if (prm.nominal) {
-                    const double e = (double)x[r0 + a] - (double)ld_stream(prm.nominal + (t * NX + r0 + a) * S + s);
+                    const double e = (double)xq[a] - (double)ld_stream(prm.nominal + (t * NX + r0 + a) * S + s);
                     acc_nom[a] += e * e;
                 }
             }
@@ -429,10 +471,12 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 
     status = quad_or(status);
     if (!active) return;
+    Real xf[3];
+    own3(x, q, xf);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const int row = r0 + a;
-        if (prm.x_final) prm.x_final[row * N + i] = x[row];
+        if (prm.x_final) prm.x_final[row * N + i] = xf[a];
         if (prm.P_final) {
 #pragma unroll
             for (int c = 0; c < NX; ++c) prm.P_final[(long long)(row * NX + c) * N + i] = Pr[a][c];
@@ -444,8 +488,11 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
         if (prm.summary) {
             Real *sm = prm.summary + i;
             const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
-            sm[(long long)row * N] = x[row];
-            sm[(long long)(12 + row) * N] = Pr[a][row];
+            Real pd = Real(0);
+#pragma unroll
+            for (int c = 0; c < NX; ++c) pd += (c == row) ? Pr[a][c] : Real(0);
+            sm[(long long)row * N] = xf[a];
+            sm[(long long)(12 + row) * N] = pd;
             sm[(long long)(24 + row) * N] = (Real)sqrt(acc_truth[a] * invT);
             sm[(long long)(36 + row) * N] = (Real)sqrt(acc_nom[a] * invT);
         }

@@ -17,6 +17,8 @@ for spec in sys.argv[1:]:
     dt = torch.float64 if dt_name == "f64" else torch.float32
     dev = {k: torch.from_numpy(v).to("cuda", dt) for k, v in st.items()}
     kw = {}
+    if mode == "joint":
+        kw["algo"] = "joint"
     if mode == "direct":
         kw["stream_index"] = torch.arange(N, dtype=torch.int32, device="cuda") % S
     if out.startswith("summary"):
