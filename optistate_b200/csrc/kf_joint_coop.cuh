@@ -24,9 +24,11 @@ namespace okf {
 
 constexpr int JC_THREADS = 128;
 constexpr int JC_TRAJ = JC_THREADS / 4;  // trajectories per block
-constexpr int JC_VEC = 24;               // per-trajectory scratch: dinv[10] at 0..9, misc
+constexpr int JC_LD = JC_TRAJ + 1;       // padded trajectory stride of the shared arrays: the four lanes of a quad often touch
+                                         // different elements of the same trajectory, which an unpadded stride maps to one bank
+constexpr int JC_VEC = 12;               // per-trajectory scratch: dinv[10]
 template <typename Real>
-constexpr size_t jc_smem_bytes() { return (size_t)(NX * NX + NZ * NZ + JC_VEC) * JC_TRAJ * sizeof(Real); }
+constexpr size_t jc_smem_bytes() { return (size_t)(NX * NX + NZ * NZ + JC_VEC) * JC_LD * sizeof(Real); }
 
 template <typename T> __device__ __forceinline__ T quad_get(T v, int lane, int src_q) { return __shfl_sync(0xffffffffu, v, (lane & ~3) | src_q); }
 template <typename T> __device__ __forceinline__ T quad_sum(T v) {
@@ -71,42 +73,42 @@ struct NoiseView {
     __device__ __forceinline__ Real at(int e) const { return __ldg(base + e * stride + offset); }
 };
 
-// in-place inverse of the 10x10 matrix at lm_ (element (i,j) at lm_[(i*10+j)*JC_TRAJ]) by Gauss-Jordan with partial pivoting
+// in-place inverse of the 10x10 matrix at lm_ (element (i,j) at lm_[(i*10+j)*JC_LD]) by Gauss-Jordan with partial pivoting
 template <typename Real>
 __device__ __noinline__ bool invert10_inplace(Real *lm_) {
     int piv[NZ];
     bool singular = false;
     for (int c = 0; c < NZ; ++c) {
         int p = c;
-        Real best = fabs(lm_[(c * NZ + c) * JC_TRAJ]);
+        Real best = fabs(lm_[(c * NZ + c) * JC_LD]);
         for (int r = c + 1; r < NZ; ++r) {
-            const Real v = fabs(lm_[(r * NZ + c) * JC_TRAJ]);
+            const Real v = fabs(lm_[(r * NZ + c) * JC_LD]);
             if (v > best) { best = v; p = r; }
         }
         piv[c] = p;
         if (!(best > Real(0)) || !isfinite(best)) singular = true;
         if (p != c)
             for (int j = 0; j < NZ; ++j) {
-                const Real t = lm_[(c * NZ + j) * JC_TRAJ];
-                lm_[(c * NZ + j) * JC_TRAJ] = lm_[(p * NZ + j) * JC_TRAJ];
-                lm_[(p * NZ + j) * JC_TRAJ] = t;
+                const Real t = lm_[(c * NZ + j) * JC_LD];
+                lm_[(c * NZ + j) * JC_LD] = lm_[(p * NZ + j) * JC_LD];
+                lm_[(p * NZ + j) * JC_LD] = t;
             }
-        const Real pinv = Real(1) / lm_[(c * NZ + c) * JC_TRAJ];
-        lm_[(c * NZ + c) * JC_TRAJ] = Real(1);
-        for (int j = 0; j < NZ; ++j) lm_[(c * NZ + j) * JC_TRAJ] *= pinv;
+        const Real pinv = Real(1) / lm_[(c * NZ + c) * JC_LD];
+        lm_[(c * NZ + c) * JC_LD] = Real(1);
+        for (int j = 0; j < NZ; ++j) lm_[(c * NZ + j) * JC_LD] *= pinv;
         for (int r = 0; r < NZ; ++r) {
             if (r == c) continue;
-            const Real f = lm_[(r * NZ + c) * JC_TRAJ];
-            lm_[(r * NZ + c) * JC_TRAJ] = Real(0);
-            for (int j = 0; j < NZ; ++j) lm_[(r * NZ + j) * JC_TRAJ] -= f * lm_[(c * NZ + j) * JC_TRAJ];
+            const Real f = lm_[(r * NZ + c) * JC_LD];
+            lm_[(r * NZ + c) * JC_LD] = Real(0);
+            for (int j = 0; j < NZ; ++j) lm_[(r * NZ + j) * JC_LD] -= f * lm_[(c * NZ + j) * JC_LD];
         }
     }
     for (int c = NZ - 1; c >= 0; --c)
         if (piv[c] != c)
             for (int r = 0; r < NZ; ++r) {
-                const Real t = lm_[(r * NZ + c) * JC_TRAJ];
-                lm_[(r * NZ + c) * JC_TRAJ] = lm_[(r * NZ + piv[c]) * JC_TRAJ];
-                lm_[(r * NZ + piv[c]) * JC_TRAJ] = t;
+                const Real t = lm_[(r * NZ + c) * JC_LD];
+                lm_[(r * NZ + c) * JC_LD] = lm_[(r * NZ + piv[c]) * JC_LD];
+                lm_[(r * NZ + piv[c]) * JC_LD] = t;
             }
     return singular;
 }
@@ -121,15 +123,15 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
     const bool active = i_raw < N;
     const long long i = active ? i_raw : N - 1;
     const long long s = stream_of(prm, i);
-    Real *pf_ = reinterpret_cast<Real *>(jc_raw) + tj;   // full P of this trajectory: element e at pf_[e * JC_TRAJ]
+    Real *pf_ = reinterpret_cast<Real *>(jc_raw) + tj;   // full P of this trajectory: element e at pf_[e * JC_LD]
     Real *lm_ = pf_ + NX * NX * JC_TRAJ;                  // S, then its Cholesky factor / inverse (10x10)
     Real *vc_ = lm_ + NZ * NZ * JC_TRAJ;                  // dinv[10]
-#define PF(e) pf_[(e) * JC_TRAJ]
-#define LM(e) lm_[(e) * JC_TRAJ]
-#define VC(e) vc_[(e) * JC_TRAJ]
+#define PF(e) pf_[(e) * JC_LD]
+#define LM(e) lm_[(e) * JC_LD]
+#define VC(e) vc_[(e) * JC_LD]
 
     const NoiseView<Real> Qv(prm.Q, prm.q_kind, N, i), Rv(prm.R, prm.r_kind, N, i);
-    Real Pr[3][NX], Kr[3][NZ], x[NX];
+    Real Pr[3][NX], x[NX];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -138,8 +140,6 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
             Pr[a][b] = prm.p0_kind == OPTI_KF_MAT_NONE ? mat_at(prm.Q, prm.q_kind, NX, row, b, N, i)
                                                         : mat_at(prm.P0, prm.p0_kind, NX, row, b, N, i);
         }
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) Kr[a][j] = Real(0);
     }
 #pragma unroll
     for (int c = 0; c < NX; ++c) x[c] = prm.x0[c * prm.x0_ld + i * prm.x0_inc];
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                 }
             }
             asym = quad_or(asym);
+            Real Kr[3][NZ];  // this lane's rows of the gain
             Real y[NZ];
 #pragma unroll
             for (int j = 0; j < NZ; ++j) y[j] = z[j] - x[sel(j)];
@@ -380,8 +381,10 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                 status |= OPTI_KF_ST_ASYMMETRIC;
                 if (q == 0 && invert10_inplace(lm_)) status |= OPTI_KF_ST_NOT_PD;
                 __syncwarp();
+#pragma unroll
                 for (int a = 0; a < NZ; ++a) {
                     Real v = Real(0);
+#pragma unroll
                     for (int b = 0; b < NZ; ++b) v += LM(a * NZ + b) * y[b];
                     nis += y[a] * v;
                 }
@@ -428,6 +431,12 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
             ptrace = quad_sum(own_trace());
             kgain = quad_sum(g);
             ymax = fmax(ymax, nis);
+            if (active && prm.K_final && t + 1 == prm.T) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int j = 0; j < NZ; ++j) prm.K_final[(long long)((r0 + a) * NZ + j) * N + i] = Kr[a][j];
+            }
         }
         Real xq[3];
         own3(x, q, xq);
@@ -471,6 +480,9 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
 
     status = quad_or(status);
     if (!active) return;
+    if (prm.K_final && !(prm.phases & OPTI_KF_PHASE_UPDATE)) {  // no update ran: the gain is defined as zero
+        for (int e = 0; e < 3 * NZ; ++e) prm.K_final[(long long)(r0 * NZ + e) * N + i] = Real(0);
+    }
     Real xf[3];
     own3(x, q, xf);
 #pragma unroll
@@ -480,10 +492,6 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
         if (prm.P_final) {
 #pragma unroll
             for (int c = 0; c < NX; ++c) prm.P_final[(long long)(row * NX + c) * N + i] = Pr[a][c];
-        }
-        if (prm.K_final) {
-#pragma unroll
-            for (int j = 0; j < NZ; ++j) prm.K_final[(long long)(row * NZ + j) * N + i] = Kr[a][j];
         }
         if (prm.summary) {
             Real *sm = prm.summary + i;
