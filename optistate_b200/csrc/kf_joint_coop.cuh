@@ -4,7 +4,7 @@
 //
 //   * Lane q of a trajectory's quad owns rows 3q..3q+2 of P (36 scalars) and of K (30 scalars) in registers; the state x
 //     is replicated in the four lanes.  32 trajectories per 128-thread block; a quad never spans two warps, so all
-//     synchronisation is __syncwarp() and warp shuffles.
+//     synchronisation is quad-wide __syncwarp(mask) and shuffles.
 //   * Row operations are local, column/row exchanges go through shuffles (F_d P needs rows 6..11 in lanes 0/1, the state
 //     update is an all-gather of 3 entries per lane) or through a per-trajectory shared-memory copy of P (the old rows
 //     P[sel,:] that P - K (H P) needs, S = H P H^T + R, and the dense predict_mpc transition).
@@ -30,17 +30,21 @@ constexpr int JC_VEC = 12;               // per-trajectory scratch: dinv[10]
 template <typename Real>
 constexpr size_t jc_smem_bytes() { return (size_t)(NX * NX + NZ * NZ + JC_VEC) * JC_LD * sizeof(Real); }
 
-template <typename T> __device__ __forceinline__ T quad_get(T v, int lane, int src_q) { return __shfl_sync(0xffffffffu, v, (lane & ~3) | src_q); }
+// Quads are independent of each other (one may take the pivoted-LU path while its neighbours do not), so every
+// shuffle and every barrier names only the four lanes of the quad.
+__device__ __forceinline__ unsigned quad_mask() { return 0xFu << ((threadIdx.x & 31) & ~3); }
+template <typename T> __device__ __forceinline__ T quad_get(T v, int lane, int src_q) { return __shfl_sync(quad_mask(), v, (lane & ~3) | src_q); }
 template <typename T> __device__ __forceinline__ T quad_sum(T v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(quad_mask(), v, 1);
+    v += __shfl_xor_sync(quad_mask(), v, 2);
     return v;
 }
 __device__ __forceinline__ uint32_t quad_or(uint32_t v) {
-    v |= __shfl_xor_sync(0xffffffffu, v, 1);
-    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    v |= __shfl_xor_sync(quad_mask(), v, 1);
+    v |= __shfl_xor_sync(quad_mask(), v, 2);
     return v;
 }
+__device__ __forceinline__ void quad_sync() { __syncwarp(quad_mask()); }
 
 template <typename Real>
 __device__ __forceinline__ Real mat_at(const Real *M, int kind, int n, int a, int b, long long N, long long i) {
@@ -206,12 +210,12 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                     if (r >= 3 && r < 6 && m == r + 6) return e1;
                     return Real(1);
                 };
-                __syncwarp();
+                quad_sync();
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int c = 0; c < NX; ++c) PF((r0 + a) * NX + c) = Pr[a][c];
-                __syncwarp();
+                quad_sync();
                 Real W[3][NX];
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
@@ -283,12 +287,12 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
         Real nis = Real(0);
         if (prm.phases & OPTI_KF_PHASE_UPDATE) {
             // all-gather of P (pre-update): S and the old rows P[sel,:] are read from this copy
-            __syncwarp();
+            quad_sync();
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int c = 0; c < NX; ++c) PF((r0 + a) * NX + c) = Pr[a][c];
-            __syncwarp();
+            quad_sync();
             // S = P[sel,sel] + R: lane q forms rows q, q+4, q+8
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                     }
                 }
             }
-            __syncwarp();
+            quad_sync();
             uint32_t asym = 0;
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
                         }
                     }
                     if (q == 0) VC(j) = dinv;
-                    __syncwarp();
+                    quad_sync();
                 }
                 // NIS = |L^-1 y|^2 (replicated) and the three K rows of this lane: L u = P[i,sel]^T, then L^T k = u
                 {
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
             } else {
                 status |= OPTI_KF_ST_ASYMMETRIC;
                 if (q == 0 && invert10_inplace(lm_)) status |= OPTI_KF_ST_NOT_PD;
-                __syncwarp();
+                quad_sync();
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) {
                     Real v = Real(0);
