@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_
     const long long i = active ? i_raw : N - 1;
     const long long s = stream_of(prm, i);
     Real *pf_ = reinterpret_cast<Real *>(jc_raw) + tj;   // full P of this trajectory: element e at pf_[e * JC_LD]
-    Real *lm_ = pf_ + NX * NX * JC_TRAJ;                  // S, then its Cholesky factor / inverse (10x10)
-    Real *vc_ = lm_ + NZ * NZ * JC_TRAJ;                  // dinv[10]
+    Real *lm_ = pf_ + NX * NX * JC_LD;                    // S, then its Cholesky factor / inverse (10x10)
+    Real *vc_ = lm_ + NZ * NZ * JC_LD;                    // dinv[10]
 #define PF(e) pf_[(e) * JC_LD]
 #define LM(e) lm_[(e) * JC_LD]
 #define VC(e) vc_[(e) * JC_LD]
