@@ -7,7 +7,6 @@
 
 #include "kf_features.cuh"
 #include "kf_identify.cuh"
-#include "kf_joint.cuh"
 #include "kf_joint_coop.cuh"
 #include "kf_seq.cuh"
 #include "kf_seq_tma.cuh"
@@ -229,11 +228,7 @@ int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
         else
             okf::kf_seq_kernel<Real, false><<<blocks, kThreads, smem, stream>>>(p);
     } else {
-        if (std::getenv("OPTISTATE_KF_JOINT_SCALAR")) {  // the one-thread-per-trajectory version, kept for A/B comparison
-            constexpr int kThreads = 64;
-            const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);
-            okf::kf_joint_kernel<Real><<<blocks, kThreads, 0, stream>>>(p);
-        } else {
+        {
             const size_t smem = okf::jc_smem_bytes<Real>();
             auto kern = okf::kf_joint_coop_kernel<Real>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;

@@ -118,7 +118,7 @@ __device__ __noinline__ bool invert10_inplace(Real *lm_) {
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(JC_THREADS) kf_joint_coop_kernel(const __grid_constant__ Params<Real> prm) {
+__global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_joint_coop_kernel(const __grid_constant__ Params<Real> prm) {
     extern __shared__ __align__(16) unsigned char jc_raw[];
     const int tid = threadIdx.x, lane = tid & 31, q = tid & 3, tj = tid >> 2;
     const int r0 = 3 * q;  // first row owned by this lane
