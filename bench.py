@@ -318,6 +318,30 @@ def run_native(a):
     value = steps_total / (ms * 1e-3)
     status_bad = int((out["status"] != 0).sum().item())
 
+    # secondary figures (rank 0, one GPU, outside the timed region; reported next to the headline, never part of it):
+    # BASELINE configs[1] - 1,024 trajectories x 10,000 steps, FP64, per-step state dump (a latency case: 32 warps in
+    # flight) - and the general JOINT path (reference operand order, four lanes per trajectory) on 131,072 trajectories
+    secondary = None
+    if rank == 0 and a.dtype == "f64":
+        def once(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3
+        reps = max(1, 10000 // T)  # the 1,000-step streams repeated in time: the data content does not matter for the rate
+        st2 = {k: d[k][:, :, :1024].repeat(reps, 1, 1).contiguous() for k in ("imu", "p", "dp", "contact", "f")}
+        t2 = once(lambda: kf_batch(st2["imu"], st2["p"], st2["dp"], st2["contact"], st2["f"], outputs=("x_steps", "p_trace", "k_gain")))
+        tj = once(lambda: kf_batch(d["imu"][:200], d["p"][:200], d["dp"][:200], d["contact"][:200], d["f"][:200], n_traj=1 << 17,
+                                   algo="joint", outputs=("x_final",)))
+        n2, T2 = st2["imu"].shape[2], st2["imu"].shape[0]
+        del st2
+        secondary = {"cfg2_1024x10k_f64_steps_per_s": n2 * T2 / t2, "cfg2_seconds": t2,
+                     "joint_path_f64_steps_per_s": (1 << 17) * 200 / tj}
+
     e2e = None
     if not a.no_e2e:
         from optistate_b200.pipeline import KfHostPipeline
@@ -358,7 +382,7 @@ def run_native(a):
             "theoretical_peak_tflops": theoretical_tf, "frac_of_theoretical": achieved_tf / theoretical_tf,
             "hbm_peak_gbs": _hbm_peak(),
         },
-        "status_nonzero_trajectories": status_bad,
+        "status_nonzero_trajectories": status_bad, "secondary": secondary,
     }
     if world == 1 and not a.no_cpu_baseline:
         v, info = cpu_port_rate(a)
