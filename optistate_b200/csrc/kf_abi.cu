@@ -48,7 +48,7 @@ bool sequential_ok(const OptiKfDesc *d) {
 
 int resolve(const OptiKfDesc *d) {
     if (d->algo == OPTI_KF_ALGO_JOINT) return OPTI_KF_ALGO_JOINT;
-    if (d->algo == OPTI_KF_ALGO_SEQUENTIAL) return sequential_ok(d) ? OPTI_KF_ALGO_SEQUENTIAL : OPTI_KF_E_UNSUPPORTED;
+    if (d->algo == OPTI_KF_ALGO_SEQUENTIAL) return sequential_ok(d) ? (int)OPTI_KF_ALGO_SEQUENTIAL : (int)OPTI_KF_E_UNSUPPORTED;
     // AUTO: a dense P0 may be non-symmetric, which only JOINT reproduces; the host asks for SEQUENTIAL explicitly
     // once it has checked symmetry.
     const bool p0_sym = d->p0_kind == OPTI_KF_MAT_NONE || is_diag_kind(d->p0_kind);
