@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     Real ptrace = Real(0), kgain = Real(0), ymax = Real(0);
     constexpr int kAccRegs = (kSummary && !kAccSmem) ? TMA_ACC_ROWS : 1;
     AccT acc_r[kAccRegs];
+#pragma unroll
+    for (int c = 0; c < kAccRegs; ++c) acc_r[c] = acc_zero(AccT());
     auto acc_add = [&](int idx, AccT v) {  // running sums: 0-11 truth, 12-23 nominal, 24 NIS
         if constexpr (kAccSmem) acc_s[idx * nt] = acc_s[idx * nt] + v;
         else if constexpr (kSummary) acc_r[idx] = acc_r[idx] + v;
