@@ -139,3 +139,18 @@ def test_identification_restatement_matches_reference_class_including_z_aliasing
     assert np.abs(q / q_ref - 1).max() < 1e-12 and np.abs(r / r_ref - 1).max() < 1e-12
     q2, r2 = identify_numpy.identify(gt, s["imu"], s["p"], s["dp"], s["contact"], s["f"], alias_last_measurement=False)
     assert np.allclose(q2, q) and not np.allclose(r2, r)  # the aliasing only changes R
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="exercises the pre-launch argument checks only")
+def test_kf_batch_rejects_inconsistent_arguments_before_touching_the_device():
+    """Shape errors are raised by the host layer; without a GPU the first thing kf_batch does is refuse to run."""
+    from optistate_b200 import kf_batch
+    from optistate_b200.batch import _stream_tensor
+
+    cpu = torch.device("cpu")
+    with pytest.raises(ValueError, match=r"\[T, 6, S\]"):
+        _stream_tensor(np.zeros((5, 7, 2)), 6, "imu", torch.float64, cpu)
+    t, T, S = _stream_tensor(np.zeros((5, 6)), 6, "imu", torch.float64, cpu)  # a single stream may omit the last axis
+    assert (T, S) == (5, 1) and t.shape == (5, 6, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kf_batch(np.zeros((5, 6, 1)), np.zeros((5, 12, 1)), np.zeros((5, 12, 1)), np.ones((5, 4, 1)), np.zeros((5, 12, 1)))

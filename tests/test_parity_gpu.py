@@ -374,3 +374,23 @@ def test_host_pipeline_matches_plain_call_and_overlaps_slots():
         want.append(ref)
     pipe.drain()
     assert torch.equal(pipe.result(tickets[-1]), want[-1])
+
+
+@pytest.mark.parametrize("algo", ["sequential", "joint"])
+def test_custom_model_constants_and_degenerate_sizes(algo):
+    """dt / mass / inertia / gravity are call arguments (the reference reads them from settings.INITIAL_PARAMS); empty and
+    single-element batches are legal."""
+    st = make_streams(range(5), 40)
+    consts = dict(dt=0.004, mass=12.5, inertia=(0.07, 0.05, 0.11), gravity=-3.71)
+    ref = c_oracle.run(st, want=("x_steps", "P_final"), **consts)
+    res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], algo=algo, outputs=("x_steps", "P_final"), **consts)
+    assert parity.rel_err(res.x_steps.cpu().numpy(), ref["x_steps"]) < 1e-10
+    assert parity.rel_err(res.P_final.cpu().numpy(), ref["P_final"]) < 1e-10
+    one = kf_batch(st["imu"][:1, :, :1], st["p"][:1, :, :1], st["dp"][:1, :, :1], st["contact"][:1, :, :1], st["f"][:1, :, :1],
+                   algo=algo, outputs=("x_steps", "final"), **consts)
+    assert parity.rel_err(one.x_steps[0, :, 0].cpu().numpy(), ref["x_steps"][0, :, 0]) < 1e-12
+    empty_t = kf_batch(st["imu"][:0], st["p"][:0], st["dp"][:0], st["contact"][:0], st["f"][:0], algo=algo, outputs=("x_steps", "final"))
+    assert empty_t.x_steps.shape == (0, 12, 5)
+    assert np.allclose(empty_t.x_final.cpu().numpy(), cases.START[:, None]) and np.allclose(empty_t.P_matrix()[0].cpu().numpy(), cases.Q_DEFAULT)
+    empty_n = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], n_traj=0, algo=algo, outputs=("x_final",))
+    assert empty_n.x_final.shape == (12, 0)
