@@ -28,12 +28,13 @@ int validate(const OptiKfDesc *d) {
     if (d->cov_model != OPTI_KF_COV_PREDICT && d->cov_model != OPTI_KF_COV_MPC) return OPTI_KF_E_SHAPE;
     if (!valid_kind(d->q_kind, false) || !valid_kind(d->r_kind, false) || !valid_kind(d->p0_kind, true)) return OPTI_KF_E_SHAPE;
     if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0)) return OPTI_KF_E_SHAPE;
-    if (!d->x0 || !d->Q || !d->R) return OPTI_KF_E_NULL;
-    if (d->p0_kind != OPTI_KF_MAT_NONE && !d->P0) return OPTI_KF_E_NULL;
-    if ((d->phases & OPTI_KF_PHASE_MEASURE) && (!d->imu || !d->p || !d->dp || !d->contact)) return OPTI_KF_E_NULL;
-    if ((d->phases & OPTI_KF_PHASE_PREDICT) && (!d->p || !d->f)) return OPTI_KF_E_NULL;
-    if ((d->phases & OPTI_KF_PHASE_UPDATE) && !(d->phases & OPTI_KF_PHASE_MEASURE) && !d->z_in) return OPTI_KF_E_NULL;
-    if (d->cov_model == OPTI_KF_COV_MPC && (d->phases & OPTI_KF_PHASE_PREDICT) && !d->body_ref) return OPTI_KF_E_NULL;
+    const bool work = d->n_traj > 0, steps = work && d->n_steps > 0;  // empty batches carry empty (NULL) arrays
+    if (work && (!d->x0 || !d->Q || !d->R)) return OPTI_KF_E_NULL;
+    if (work && d->p0_kind != OPTI_KF_MAT_NONE && !d->P0) return OPTI_KF_E_NULL;
+    if (steps && (d->phases & OPTI_KF_PHASE_MEASURE) && (!d->imu || !d->p || !d->dp || !d->contact)) return OPTI_KF_E_NULL;
+    if (steps && (d->phases & OPTI_KF_PHASE_PREDICT) && (!d->p || !d->f)) return OPTI_KF_E_NULL;
+    if (steps && (d->phases & OPTI_KF_PHASE_UPDATE) && !(d->phases & OPTI_KF_PHASE_MEASURE) && !d->z_in) return OPTI_KF_E_NULL;
+    if (steps && d->cov_model == OPTI_KF_COV_MPC && (d->phases & OPTI_KF_PHASE_PREDICT) && !d->body_ref) return OPTI_KF_E_NULL;
     if (d->P_ckpt && d->ckpt_every == 0) return OPTI_KF_E_SHAPE;
     if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     return OPTI_KF_OK;
