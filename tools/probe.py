@@ -40,7 +40,9 @@ def main():
             for algo in ("sequential", "joint"):
                 if algo == "joint" and N > 160000:
                     continue
-                for outs in (("x_final",), ("summary",)) if algo == "sequential" else (("x_final",),):
+                for outs in (("x_final",), ("summary",), ("x_steps",)) if algo == "sequential" else (("x_final",),):
+                    if outs == ("x_steps",) and N * T * 12 * (8 if name == "f64" else 4) > 40e9:
+                        continue
                     kw = dict(truth=dev["truth"]) if outs == ("summary",) else {}
                     fn = lambda: kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], n_traj=N, dtype=dt, algo=algo, outputs=outs, **kw)  # noqa: E731
                     s = timed(fn)
