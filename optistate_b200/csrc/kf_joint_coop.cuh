@@ -63,6 +63,25 @@ __device__ __forceinline__ void own3(const Real (&v)[NX], int q, Real (&o)[3]) {
     for (int a = 0; a < 3; ++a) o[a] = q == 0 ? v[a] : q == 1 ? v[3 + a] : q == 2 ? v[6 + a] : v[9 + a];
 }
 
+// Diagonal entry P[3q+a][3q+a] of lane q's row a.  Written as a select chain over compile-time indices: a loop of the
+// form "sum_c (c == 3q+a) ? Pr[a][c] : 0" is recognised by the compiler as Pr[a][3q+a], a dynamic register index that
+// would push the whole array into local memory.
+template <typename Real>
+__device__ __forceinline__ Real own_diag(const Real (&Pr)[3][NX], int q, int a) {
+    return q == 0 ? Pr[a][a] : q == 1 ? Pr[a][3 + a] : q == 2 ? Pr[a][6 + a] : Pr[a][9 + a];
+}
+template <typename Real>
+__device__ __forceinline__ Real own_trace(const Real (&Pr)[3][NX], int q) {
+    return own_diag(Pr, q, 0) + own_diag(Pr, q, 1) + own_diag(Pr, q, 2);
+}
+template <typename Real>
+__device__ __forceinline__ void add_own_diag(Real (&Pr)[3][NX], int q, int a, Real v) {
+    Pr[a][a] += q == 0 ? v : Real(0);
+    Pr[a][3 + a] += q == 1 ? v : Real(0);
+    Pr[a][6 + a] += q == 2 ? v : Real(0);
+    Pr[a][9 + a] += q == 3 ? v : Real(0);
+}
+
 // noise matrices without per-element switches: element e of a dense matrix / entry a of a diagonal lives at
 // base[e * stride + offset] with (stride, offset) = (1, 0) for a shared array and (N, i) for a per-trajectory one
 template <typename Real>
@@ -150,15 +169,7 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
 
     uint32_t status = 0;
     Real ptrace = Real(0), kgain = Real(0), ymax = Real(0);
-    auto own_trace = [&]() {  // sum of this lane's diagonal entries P[3q+a][3q+a], compile-time register indices only
-        Real d = Real(0);
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int c = 0; c < NX; ++c) d += (c == r0 + a) ? Pr[a][c] : Real(0);
-        return d;
-    };
-    ptrace = quad_sum(own_trace());
+    ptrace = quad_sum(own_trace(Pr, q));
     double acc_truth[3] = {0.0, 0.0, 0.0}, acc_nom[3] = {0.0, 0.0, 0.0}, acc_nis = 0.0;
 
     for (long long t = 0; t < prm.T; ++t) {
@@ -233,8 +244,12 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                         Real acc = Real(0);
 #pragma unroll
                         for (int m = 0; m < NX; ++m) acc += W[a][m] * fd(c, m);
-                        Pr[a][c] = acc + (Qv.dense ? Qv.at((r0 + a) * NX + c) : (c == r0 + a ? Qv.at(r0 + a) : Real(0)));
+                        Pr[a][c] = acc + (Qv.dense ? Qv.at((r0 + a) * NX + c) : Real(0));
                     }
+                if (!Qv.dense) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) add_own_diag(Pr, q, a, Qv.at(r0 + a));
+                }
                 propagate_mean(prm, x, pf, ff, Rm);
             } else {
                 propagate_mean(prm, x, pf, ff, Rm);
@@ -263,13 +278,11 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
 #pragma unroll
                         for (int c = 0; c < NX; ++c) Pr[a][c] += Qv.at((r0 + a) * NX + c);
                     } else {
-                        const Real qd = Qv.at(r0 + a);
-#pragma unroll
-                        for (int c = 0; c < NX; ++c) Pr[a][c] += (c == r0 + a) ? qd : Real(0);
+                        add_own_diag(Pr, q, a, Qv.at(r0 + a));
                     }
                 }
             }
-            ptrace = quad_sum(own_trace());
+            ptrace = quad_sum(own_trace(Pr, q));
             if (active && prm.x_model_steps) {
                 Real xo[3];
                 own3(x, q, xo);
@@ -427,12 +440,11 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                     const Real ps = PF(sel(j) * NX + c);
                     Pr[0][c] -= Kr[0][j] * ps; Pr[1][c] -= Kr[1][j] * ps; Pr[2][c] -= Kr[2][j] * ps;
                 }
-            Real g = Real(0);  // np.trace of the 12x10 gain: K[j][j], j < 10
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int j = 0; j < NZ; ++j) g += (j == r0 + a) ? Kr[a][j] : Real(0);
-            ptrace = quad_sum(own_trace());
+            // np.trace of the 12x10 gain: K[j][j], j < 10 (select chain over compile-time indices, see own_diag)
+            const Real g = q == 0 ? Kr[0][0] + Kr[1][1] + Kr[2][2]
+                         : q == 1 ? Kr[0][3] + Kr[1][4] + Kr[2][5]
+                         : q == 2 ? Kr[0][6] + Kr[1][7] + Kr[2][8] : Kr[0][9];
+            ptrace = quad_sum(own_trace(Pr, q));
             kgain = quad_sum(g);
             ymax = fmax(ymax, nis);
             if (active && prm.K_final && t + 1 == prm.T) {
@@ -500,11 +512,8 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
         if (prm.summary) {
             Real *sm = prm.summary + i;
             const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
-            Real pd = Real(0);
-#pragma unroll
-            for (int c = 0; c < NX; ++c) pd += (c == row) ? Pr[a][c] : Real(0);
             sm[(long long)row * N] = xf[a];
-            sm[(long long)(12 + row) * N] = pd;
+            sm[(long long)(12 + row) * N] = own_diag(Pr, q, a);
             sm[(long long)(24 + row) * N] = (Real)sqrt(acc_truth[a] * invT);
             sm[(long long)(36 + row) * N] = (Real)sqrt(acc_nom[a] * invT);
         }
