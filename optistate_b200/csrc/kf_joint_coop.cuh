@@ -221,6 +221,14 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                     if (r >= 3 && r < 6 && m == r + 6) return e1;
                     return Real(1);
                 };
+                // F_d[3q + a][k] of this lane's own rows, with compile-time indices into E (rows 0..2 live in lane 0,
+                // rows 3..5 in lane 1, the other rows of F_d are all ones)
+                auto fd_own = [&](int a, int k) -> Real {
+                    Real v = Real(1);
+                    if (k >= 6 && k < 9) v = q == 0 ? E[3 * a + (k - 6)] : Real(1);
+                    if (k == 9 + a) v = q == 1 ? e1 : v;
+                    return v;
+                };
                 quad_sync();
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                     for (int c = 0; c < NX; ++c) {
                         Real acc = Real(0);
 #pragma unroll
-                        for (int k = 0; k < NX; ++k) acc += fd(r0 + a, k) * PF(k * NX + c);
+                        for (int k = 0; k < NX; ++k) acc += fd_own(a, k) * PF(k * NX + c);
                         W[a][c] = acc;
                     }
 #pragma unroll
