@@ -9,7 +9,8 @@ x 1,000 steps PER GPU over 1,024 shared synthetic base streams, per-member diago
 per-trajectory summaries (final x, diag P, RMSE vs the label stream, RMS deviation from the nominal member, mean
 NIS, ...) - run in FP64 by default because the north-star target is stated on the FP64 FMA roofline with 1e-9
 parity (--dtype f32 gives configs[2] verbatim).  One "step" of the bench = one full pass of the hot path over
-that batch: measurement pre-pass + the filter kernel (+ the NCCL all-gather of the summaries when N > 1).
+that batch: measurement pre-pass + the filter kernel; when N > 1 the all-gather of the summaries is fused into the
+filter kernel (NVLink peer stores, optistate_b200/peer.py; --gather nccl runs the NCCL all-gather instead).
 
   value      whole-job trajectory-steps/s, inputs resident in HBM, timed with CUDA events, max over ranks
   e2e        same through the public kf_batch() call with pinned HOST buffers: H2D of streams + per-member noise
@@ -64,6 +65,8 @@ def parse():
     ap.add_argument("--streams", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: all-gather of the summaries fused into the filter kernel (NVLink peer stores) or NCCL after it")
     return ap.parse_args()
 
 
@@ -261,13 +264,36 @@ def run_native(a):
            "workspace": torch.empty(T * 10 * S * esz + 4 * S + 4096, dtype=torch.uint8, device=dev)}
     summary_host = torch.empty((nv.SUMMARY_ROWS, n_local), dtype=dtype).pin_memory()
 
-    def step_resident():
+    # N > 1: every GPU ends each step holding the summaries of ALL trajectories.  Default: the filter kernel stores them
+    # into every GPU's copy itself (peer.PeerSummary); --gather nccl (or no peer access on this box): NCCL all-gather
+    peer, gather_how = None, "single GPU"
+    if world > 1:
+        gather_how = "NCCL all-gather after the kernel"
+        if a.gather == "fused":
+            from optistate_b200.peer import PeerSummary
+            try:
+                peer = PeerSummary(n_total, dtype)
+                gather_how = "fused into the filter kernel (NVLink peer stores) + one 4-byte NCCL all-reduce as barrier"
+            except RuntimeError as e:  # agreed on by all ranks inside PeerSummary
+                gather_how += f" ({e})"
+
+    def step_nccl():
         res = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], Q=d["Q"], R=d["R"], n_traj=n_local, dtype=dtype,
                        stream_offset=first, truth=d["truth"], nominal=d["nominal"], outputs=("summary",), out=out,
                        q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER)
         if world > 1:
             return gather_columns(res.summary, n_total)
         return res.summary
+
+    def step_fused():
+        peer.wait()  # every rank is done with the previous step's gathered array
+        kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], Q=d["Q"], R=d["R"], n_traj=n_local, dtype=dtype,
+                 stream_offset=first, truth=d["truth"], nominal=d["nominal"], outputs=("summary",), out=out,
+                 q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, summary_peers=peer)
+        peer.wait()  # all kernels have finished: peer.tensor holds all n_total columns on every GPU
+        return peer.tensor
+
+    step_resident = step_fused if peer is not None else step_nccl
 
     # end-to-end through the public host-buffer API: every step uploads ALL of its inputs from pinned host memory and
     # downloads its summaries; the double-buffered pipeline overlaps step k+1's upload and step k-1's download with step
@@ -317,6 +343,19 @@ def run_native(a):
     steps_total = n_total * T * a.steps
     value = steps_total / (ms * 1e-3)
     status_bad = int((out["status"] != 0).sum().item())
+    gather_info = None
+    if world > 1:
+        gather_info = {"how": gather_how}
+        if peer is not None:
+            # the same job with the NCCL all-gather, and a check that the two gathered arrays are identical
+            fused_copy = peer.tensor.clone()
+            for _ in range(2):
+                ref = step_nccl()
+            gather_info["identical_to_nccl_gather"] = bool(torch.equal(fused_copy, ref))
+            ms_n, _ = timed(step_nccl, a.steps)
+            gather_info["nccl_gather_value"] = steps_total / (ms_n * 1e-3)
+            gather_info["nccl_gather_ms_per_step"] = ms_n / a.steps
+            del fused_copy, ref
 
     # secondary figures (rank 0, one GPU, outside the timed region; reported next to the headline, never part of it):
     # BASELINE configs[1] - 1,024 trajectories x 10,000 steps, FP64, per-step state dump (a latency case: 32 warps in
@@ -356,6 +395,8 @@ def run_native(a):
                "d2h_bytes_per_step": summary_host.numel() * summary_host.element_size() * world, "ms_per_step": ms_e / a.steps,
                "api": "optistate_b200.pipeline.KfHostPipeline (kf_batch on pinned host buffers, double-buffered)"}
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,6 +425,9 @@ def run_native(a):
         },
         "status_nonzero_trajectories": status_bad, "secondary": secondary,
     }
+    if gather_info is not None:
+        line["gather"] = gather_info
+        line["config"]["sharding"] = f"contiguous blocks x{world}; summaries gathered on every GPU: {gather_how}"
     if world == 1 and not a.no_cpu_baseline:
         v, info = cpu_port_rate(a)
         line["cpu_baseline"] = dict({"value": v, "unit": UNIT}, **info)

@@ -39,11 +39,13 @@
 extern "C" {
 #endif
 
-#define OPTISTATE_KF_ABI_VERSION 1
+#define OPTISTATE_KF_ABI_VERSION 2
 
 #define OPTI_KF_NX 12 /* states  [thx thy thz | x y z | wx wy wz | vx vy vz]   kalman_filter.py:9  */
 #define OPTI_KF_NZ 10 /* measurements [th_imu(3) z_odom w_imu(3) v_odom(3)]    kalman_filter.py:11 */
 #define OPTI_KF_SUMMARY_ROWS 52
+#define OPTI_KF_MAX_PEERS 7        /* other GPUs of one NVSwitch box */
+#define OPTI_KF_PEER_HANDLE_BYTES 64
 
 /* dtype */
 enum { OPTI_KF_F64 = 0, OPTI_KF_F32 = 1 };
@@ -143,6 +145,18 @@ typedef struct OptiKfDesc {
        the per-step inputs with TMA; without it the measurement is formed inside the filter kernel */
     void *workspace;
     size_t workspace_bytes;
+
+    /* multi-GPU: the all-gather of the summaries fused into the filter kernel.  `summary` points at this rank's first
+       column inside a [OPTI_KF_SUMMARY_ROWS][summary_ld] array (summary_ld = trajectories of the whole job; 0 means
+       n_traj, the single-GPU layout), and every summary_peers[k] at the same column of the same array in another
+       GPU's memory, mapped into this process (optistate_kf_peer_open).  The kernel stores each summary value to all
+       of them, so when the kernels of all ranks have finished every GPU holds the gathered array; the stores travel
+       over NVLink while other trajectories are still being filtered.  The caller orders "all kernels finished" with
+       a barrier of its own (one NCCL barrier in optistate_b200.distributed). */
+    int64_t summary_ld;
+    int32_t n_summary_peers; /* 0 .. OPTI_KF_MAX_PEERS */
+    int32_t reserved0;
+    void *summary_peers[OPTI_KF_MAX_PEERS];
 } OptiKfDesc;
 
 typedef struct OptiKfMeasureDesc {
@@ -220,6 +234,17 @@ int optistate_kf_workspace_bytes(const OptiKfDesc *desc, size_t *bytes_out);
 int optistate_fma_peak(int dtype, int64_t fma_per_thread, double *flops_per_s_out, double *seconds_out, void *cuda_stream);
 /* Number of kernel launches this library has made in this process (for bench.py's gpu_launches claim). */
 int64_t optistate_kf_launch_count(void);
+
+/* Peer memory for the fused summary all-gather (one process per GPU, all GPUs of one box).  optistate_kf_peer_alloc
+ * returns a dedicated device allocation on the current device (exportable: offset 0 of its own cudaMalloc);
+ * _export fills an opaque handle that another process passes to _open to map the allocation into its address
+ * space with peer access over NVLink (cudaIpc*, lazy peer enable); _close unmaps, _free releases. */
+int optistate_kf_peer_alloc(size_t bytes, void **dev_ptr_out);
+int optistate_kf_peer_free(void *dev_ptr);
+int optistate_kf_peer_export(void *dev_ptr, unsigned char handle_out[OPTI_KF_PEER_HANDLE_BYTES]);
+int optistate_kf_peer_open(const unsigned char handle[OPTI_KF_PEER_HANDLE_BYTES], void **peer_ptr_out);
+int optistate_kf_peer_close(void *peer_ptr);
+
 const char *optistate_kf_strerror(int code);
 int optistate_kf_abi_version(void);
 size_t optistate_kf_desc_size(void);

@@ -119,6 +119,7 @@ def kf_batch(
     algo: str = "auto", cov_model: str = "predict", q_kind=None, r_kind=None, p0_kind=None,
     dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
     gravity: float = INITIAL_PARAMS.GRAVITY, device=None, out: Optional[Dict[str, torch.Tensor]] = None,
+    summary_peers=None,
 ) -> KfBatchResult:
     """Runs the Kalman filter over N trajectories x T steps on the current CUDA device.
 
@@ -130,6 +131,10 @@ def kf_batch(
     (k_gain), nis_steps, P_ckpt (p_checkpoints, needs ckpt_every), x_final, P_final, final (= both), K_final, summary.
     algo: "auto" | "sequential" | "joint" (see include/optistate_kf.h).  cov_model: "predict" | "mpc".
     out: optional preallocated output tensors by canonical name.
+    summary_peers: an optistate_b200.peer.PeerSummary - the summary is then written into this rank's columns of the
+    job-wide [52, n_total] array on EVERY GPU of the box by the filter kernel itself (fused all-gather over NVLink peer
+    stores); `result.summary` is the local column block, `summary_peers.tensor` the gathered array once
+    `summary_peers.wait()` has run.
     """
     nv.require_cuda()
     ext = nv.ext()
@@ -178,7 +183,11 @@ def kf_batch(
         if o not in _OUT_SHAPES:
             raise ValueError(f"unknown output '{o}'")
         shape = _OUT_SHAPES[o](T, N, n_ckpt)
-        if out is not None and o in out:
+        if o == "summary" and summary_peers is not None:
+            if summary_peers.dtype != dtype or summary_peers.n_local != N or summary_peers.device != device:
+                raise ValueError("summary_peers was set up for another dtype, device or shard size")
+            tensors[o] = summary_peers.tensor
+        elif out is not None and o in out:
             if tuple(out[o].shape) != shape or out[o].dtype != dtype:
                 raise ValueError(f"out['{o}'] must be {shape} {dtype}")
             tensors[o] = out[o]
@@ -191,6 +200,8 @@ def kf_batch(
                cov_model=nv.COV_MPC if cov_model == "mpc" else nv.COV_PREDICT, phases=phases, n_traj=N, n_steps=T,
                n_streams=S, stream_offset=int(stream_offset), x0_per_traj=int(x0_t.dim() == 2), p0_kind=pk, q_kind=qk,
                r_kind=rk, ckpt_every=int(ckpt_every), want_K=int("K_final" in want))
+    if summary_peers is not None and "summary" in want:
+        cfg.update(summary_peers.cfg())
     if cfg["algo"] == nv.ALGO_AUTO:
         # a symmetric dense P0 is fine for the packed-symmetric kernel; a non-symmetric one needs the joint form
         probe = dict(cfg, algo=nv.ALGO_SEQUENTIAL)
@@ -211,8 +222,10 @@ def kf_batch(
                 ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
             tensors["workspace"] = ws
         nv.check(int(ext.kf_batch(cfg, consts, tensors)), "optistate_kf_batch")
-    return KfBatchResult(algo=_ALGO_NAMES[cfg["algo"]], n_traj=N, n_steps=T,
-                         tensors={k: tensors[k] for k in want}, status=status)
+    res = {k: tensors[k] for k in want}
+    if summary_peers is not None and "summary" in res:
+        res["summary"] = summary_peers.local
+    return KfBatchResult(algo=_ALGO_NAMES[cfg["algo"]], n_traj=N, n_steps=T, tensors=res, status=status)
 
 
 def kf_measure(imu, p, dp, contact, *, dtype: torch.dtype = torch.float64, device=None, want_odom: bool = False):

@@ -37,6 +37,10 @@ int validate(const OptiKfDesc *d) {
     if (steps && d->cov_model == OPTI_KF_COV_MPC && (d->phases & OPTI_KF_PHASE_PREDICT) && !d->body_ref) return OPTI_KF_E_NULL;
     if (d->P_ckpt && d->ckpt_every == 0) return OPTI_KF_E_SHAPE;
     if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
+    if (d->summary_ld < 0 || (d->summary_ld > 0 && d->summary_ld < d->n_traj)) return OPTI_KF_E_SHAPE;
+    if (d->n_summary_peers < 0 || d->n_summary_peers > OPTI_KF_MAX_PEERS) return OPTI_KF_E_SHAPE;
+    for (int k = 0; k < d->n_summary_peers; ++k)
+        if (d->summary && !d->summary_peers[k]) return OPTI_KF_E_NULL;
     return OPTI_KF_OK;
 }
 
@@ -80,6 +84,9 @@ okf::Params<Real> make_params(const OptiKfDesc *d) {
     p.nis_steps = (Real *)d->nis_steps; p.ckpt_every = d->ckpt_every; p.P_ckpt = (Real *)d->P_ckpt;
     p.x_final = (Real *)d->x_final; p.P_final = (Real *)d->P_final; p.K_final = (Real *)d->K_final;
     p.summary = (Real *)d->summary; p.status = d->status;
+    p.summary_ld = d->summary_ld > 0 ? d->summary_ld : d->n_traj;
+    p.n_summary_peers = d->summary ? d->n_summary_peers : 0;
+    for (int k = 0; k < p.n_summary_peers; ++k) p.summary_peers[k] = (Real *)d->summary_peers[k];
     return p;
 }
 
@@ -175,6 +182,9 @@ bool packed_pair_ok(const OptiKfDesc *d) {
                           d->k_gain_steps, d->nis_steps, d->P_ckpt, d->x_final, d->P_final, d->summary};
     for (const void *q : ptrs)
         if (q && !aligned8(q)) return false;
+    if (d->summary && d->summary_ld % 2 != 0) return false;  // pairs of summary values are stored as one float2
+    for (int k = 0; k < d->n_summary_peers; ++k)
+        if (d->summary && !aligned8(d->summary_peers[k])) return false;
     return true;
 }
 
@@ -508,6 +518,42 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *d, void *cuda_stream) 
     cudaGetLastError();
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     return d->dtype == OPTI_KF_F64 ? identify_noise<double>(d, stream) : identify_noise<float>(d, stream);
+}
+
+// ---- peer memory for the fused summary all-gather (cudaIpc: one process per GPU on one box) ----
+int optistate_kf_peer_alloc(size_t bytes, void **dev_ptr_out) {
+    if (!dev_ptr_out || bytes == 0) return OPTI_KF_E_NULL;
+    *dev_ptr_out = nullptr;
+    return cudaMalloc(dev_ptr_out, bytes) == cudaSuccess ? (int)OPTI_KF_OK : (cudaGetLastError(), (int)OPTI_KF_E_CUDA);
+}
+
+int optistate_kf_peer_free(void *dev_ptr) {
+    if (!dev_ptr) return OPTI_KF_OK;
+    return cudaFree(dev_ptr) == cudaSuccess ? (int)OPTI_KF_OK : (cudaGetLastError(), (int)OPTI_KF_E_CUDA);
+}
+
+int optistate_kf_peer_export(void *dev_ptr, unsigned char handle_out[OPTI_KF_PEER_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= OPTI_KF_PEER_HANDLE_BYTES, "handle does not fit");
+    if (!dev_ptr || !handle_out) return OPTI_KF_E_NULL;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, dev_ptr) != cudaSuccess) { cudaGetLastError(); return OPTI_KF_E_CUDA; }
+    std::memset(handle_out, 0, OPTI_KF_PEER_HANDLE_BYTES);
+    std::memcpy(handle_out, &h, sizeof h);
+    return OPTI_KF_OK;
+}
+
+int optistate_kf_peer_open(const unsigned char handle[OPTI_KF_PEER_HANDLE_BYTES], void **peer_ptr_out) {
+    if (!handle || !peer_ptr_out) return OPTI_KF_E_NULL;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    *peer_ptr_out = nullptr;
+    if (cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return OPTI_KF_E_CUDA; }
+    return OPTI_KF_OK;
+}
+
+int optistate_kf_peer_close(void *peer_ptr) {
+    if (!peer_ptr) return OPTI_KF_OK;
+    return cudaIpcCloseMemHandle(peer_ptr) == cudaSuccess ? (int)OPTI_KF_OK : (cudaGetLastError(), (int)OPTI_KF_E_CUDA);
 }
 
 const char *optistate_kf_strerror(int code) {

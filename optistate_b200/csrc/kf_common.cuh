@@ -32,7 +32,20 @@ struct Params {
     Real *P_ckpt, *x_final, *P_final, *K_final, *summary;
     uint32_t *status;
     const uint32_t *stream_status;  // [S] per-stream flags of the measurement pre-pass, OR-ed into status
+    // fused all-gather of the summaries: rows are summary_ld apart (the whole job's trajectory count) and every value
+    // is stored to the same element of each peer GPU's copy as well (NVLink stores, OptiKfDesc.summary_peers)
+    long long summary_ld;
+    int n_summary_peers;
+    Real *summary_peers[OPTI_KF_MAX_PEERS];
 };
+
+// One summary value of trajectory i (or of the pair i, i+1 for the packed FP32 type): local copy plus every peer copy.
+template <typename Real, typename V>
+__device__ __forceinline__ void st_summary(const Params<Real> &prm, int row, long long i, V v) {
+    const long long idx = (long long)row * prm.summary_ld + i;
+    st_traj(prm.summary, idx, v);
+    for (int k = 0; k < prm.n_summary_peers; ++k) st_traj(prm.summary_peers[k], idx, v);
+}
 
 // sin and cos of an attitude angle, straight-line (no slow-path branch, so the trigonometry of the NEXT step can be
 // scheduled underneath the rank-1 FMAs of the current one): Cody-Waite reduction by pi/2 with fused steps, then the

@@ -518,22 +518,20 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
             for (int c = 0; c < NX; ++c) prm.P_final[(long long)(row * NX + c) * N + i] = Pr[a][c];
         }
         if (prm.summary) {
-            Real *sm = prm.summary + i;
             const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
-            sm[(long long)row * N] = xf[a];
-            sm[(long long)(12 + row) * N] = own_diag(Pr, q, a);
-            sm[(long long)(24 + row) * N] = (Real)sqrt(acc_truth[a] * invT);
-            sm[(long long)(36 + row) * N] = (Real)sqrt(acc_nom[a] * invT);
+            st_summary(prm, row, i, xf[a]);
+            st_summary(prm, 12 + row, i, own_diag(Pr, q, a));
+            st_summary(prm, 24 + row, i, (Real)sqrt(acc_truth[a] * invT));
+            st_summary(prm, 36 + row, i, (Real)sqrt(acc_nom[a] * invT));
         }
     }
     if (q == 0) {
         if (prm.summary) {
-            Real *sm = prm.summary + i;
             const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
-            sm[48LL * N] = (Real)(acc_nis * invT);
-            sm[49LL * N] = ptrace;
-            sm[50LL * N] = kgain;
-            sm[51LL * N] = (Real)sqrt((double)ymax);
+            st_summary(prm, 48, i, (Real)(acc_nis * invT));
+            st_summary(prm, 49, i, ptrace);
+            st_summary(prm, 50, i, kgain);
+            st_summary(prm, 51, i, (Real)sqrt((double)ymax));
         }
         if (prm.status) prm.status[i] = status;
     }

@@ -160,19 +160,18 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
             for (int b = 0; b < NX; ++b) prm.P_final[(long long)(a * NX + b) * N + i] = P[tri(a, b)];
     }
     if (kSummary && prm.summary) {
-        Real *sm = prm.summary + i;
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            sm[(long long)c * N] = x[c];
-            sm[(long long)(12 + c) * N] = P[tri(c, c)];
-            sm[(long long)(24 + c) * N] = (Real)sqrt(acc_truth[c] * invT);
-            sm[(long long)(36 + c) * N] = (Real)sqrt(acc_nom[c] * invT);
+            st_summary(prm, c, i, x[c]);
+            st_summary(prm, 12 + c, i, P[tri(c, c)]);
+            st_summary(prm, 24 + c, i, (Real)sqrt(acc_truth[c] * invT));
+            st_summary(prm, 36 + c, i, (Real)sqrt(acc_nom[c] * invT));
         }
-        sm[48LL * N] = (Real)(acc_nis * invT);
-        sm[49LL * N] = ptrace;
-        sm[50LL * N] = kgain;
-        sm[51LL * N] = (Real)sqrt((double)ymax);
+        st_summary(prm, 48, i, (Real)(acc_nis * invT));
+        st_summary(prm, 49, i, ptrace);
+        st_summary(prm, 50, i, kgain);
+        st_summary(prm, 51, i, (Real)sqrt((double)ymax));
     }
     if (prm.status) prm.status[i] = status[0];
 }

@@ -342,15 +342,15 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-            st_traj(prm.summary, (long long)c * N + i, x[c]);
-            st_traj(prm.summary, (long long)(12 + c) * N + i, P[tri(c, c)]);
-            st_traj(prm.summary, (long long)(24 + c) * N + i, rms_out(acc_get(c), invT, Real()));
-            st_traj(prm.summary, (long long)(36 + c) * N + i, rms_out(acc_get(12 + c), invT, Real()));
+            st_summary(prm, c, i, x[c]);
+            st_summary(prm, 12 + c, i, P[tri(c, c)]);
+            st_summary(prm, 24 + c, i, rms_out(acc_get(c), invT, Real()));
+            st_summary(prm, 36 + c, i, rms_out(acc_get(12 + c), invT, Real()));
         }
-        st_traj(prm.summary, 48LL * N + i, mean_out(acc_get(24), invT, Real()));
-        st_traj(prm.summary, 49LL * N + i, ptrace);
-        st_traj(prm.summary, 50LL * N + i, kgain);
-        st_traj(prm.summary, 51LL * N + i, sqrt_(ymax));
+        st_summary(prm, 48, i, mean_out(acc_get(24), invT, Real()));
+        st_summary(prm, 49, i, ptrace);
+        st_summary(prm, 50, i, kgain);
+        st_summary(prm, 51, i, sqrt_(ymax));
     }
     if (prm.status) {
 #pragma unroll

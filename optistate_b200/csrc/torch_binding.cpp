@@ -124,7 +124,24 @@ int64_t kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::
     d.x_final = const_cast<void *>(ck.get(tensors, "x_final", 12 * N, false));
     d.P_final = const_cast<void *>(ck.get(tensors, "P_final", 144 * N, false));
     d.K_final = const_cast<void *>(ck.get(tensors, "K_final", 120 * N, false));
-    d.summary = const_cast<void *>(ck.get(tensors, "summary", (int64_t)OPTI_KF_SUMMARY_ROWS * N, false));
+    // fused all-gather: 'summary' is then the whole job's [52][summary_ld] array, this rank owning columns
+    // [summary_col0, summary_col0 + N), and summary_peer<k> the addresses of the other GPUs' copies (peer_open)
+    d.summary_ld = geti(cfg, "summary_ld", 0);
+    const int64_t col0 = geti(cfg, "summary_col0", 0);
+    TORCH_CHECK(d.summary_ld >= 0 && col0 >= 0 && (d.summary_ld == 0 ? col0 == 0 : col0 + N <= d.summary_ld),
+                "optistate_b200: summary columns [", col0, ", ", col0 + N, ") do not fit summary_ld = ", d.summary_ld);
+    d.summary = const_cast<void *>(ck.get(tensors, "summary", (int64_t)OPTI_KF_SUMMARY_ROWS * (d.summary_ld ? d.summary_ld : N), false));
+    if (d.summary) {
+        const size_t esz = d.dtype == OPTI_KF_F64 ? 8 : 4;
+        d.summary = static_cast<char *>(d.summary) + (size_t)col0 * esz;
+        d.n_summary_peers = (int32_t)geti(cfg, "n_summary_peers", 0);
+        TORCH_CHECK(d.n_summary_peers >= 0 && d.n_summary_peers <= OPTI_KF_MAX_PEERS, "optistate_b200: at most ", OPTI_KF_MAX_PEERS, " peers");
+        for (int k = 0; k < d.n_summary_peers; ++k) {
+            const int64_t addr = geti(cfg, ("summary_peer" + std::to_string(k)).c_str(), 0);
+            TORCH_CHECK(addr != 0, "optistate_b200: summary_peer", k, " missing");
+            d.summary_peers[k] = reinterpret_cast<char *>((uintptr_t)addr) + (size_t)col0 * esz;
+        }
+    }
     {
         auto iw = tensors.find("workspace");
         if (iw != tensors.end()) {
@@ -307,6 +324,41 @@ int kf_identify_noise(int64_t dtype, int64_t n_traj, int64_t n_steps, int64_t n_
     return optistate_kf_identify_noise(&d, at::cuda::getCurrentCUDAStream().stream());
 }
 
+// ---- peer memory (fused summary all-gather) ----
+at::Tensor peer_alloc(int64_t nbytes, int64_t device_index) {
+    TORCH_CHECK(nbytes > 0, "optistate_b200: peer_alloc needs a positive size");
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device_index);
+    void *ptr = nullptr;
+    const int rc = optistate_kf_peer_alloc((size_t)nbytes, &ptr);
+    TORCH_CHECK(rc == 0, "optistate_kf_peer_alloc: ", optistate_kf_strerror(rc));
+    const int dev = (int)device_index;
+    return at::from_blob(ptr, {nbytes}, [dev](void *q) { const c10::cuda::CUDAGuard g((c10::DeviceIndex)dev); optistate_kf_peer_free(q); },
+                         at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (c10::DeviceIndex)device_index));
+}
+
+py::bytes peer_export(const at::Tensor &t) {
+    TORCH_CHECK(t.is_cuda() && t.storage_offset() == 0, "optistate_b200: peer_export needs the tensor peer_alloc returned");
+    const c10::cuda::CUDAGuard guard(t.device());
+    unsigned char h[OPTI_KF_PEER_HANDLE_BYTES];
+    const int rc = optistate_kf_peer_export(t.data_ptr(), h);
+    TORCH_CHECK(rc == 0, "optistate_kf_peer_export: ", optistate_kf_strerror(rc));
+    return py::bytes(reinterpret_cast<const char *>(h), sizeof h);
+}
+
+int64_t peer_open(const std::string &handle, int64_t device_index) {
+    TORCH_CHECK(handle.size() == OPTI_KF_PEER_HANDLE_BYTES, "optistate_b200: bad peer handle");
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device_index);
+    void *ptr = nullptr;
+    const int rc = optistate_kf_peer_open(reinterpret_cast<const unsigned char *>(handle.data()), &ptr);
+    TORCH_CHECK(rc == 0, "optistate_kf_peer_open: ", optistate_kf_strerror(rc), " (peer memory needs all ranks on one box)");
+    return (int64_t)(uintptr_t)ptr;
+}
+
+void peer_close(int64_t addr, int64_t device_index) {
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device_index);
+    optistate_kf_peer_close(reinterpret_cast<void *>((uintptr_t)addr));
+}
+
 std::pair<double, double> fma_peak(int64_t dtype, int64_t fma_per_thread) {
     double flops = 0, secs = 0;
     const int rc = optistate_fma_peak((int)dtype, fma_per_thread, &flops, &secs, at::cuda::getCurrentCUDAStream().stream());
@@ -326,9 +378,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_features", &kf_features);
     m.def("kf_minmax", &kf_minmax);
     m.def("kf_windows", &kf_windows);
+    m.def("peer_alloc", &peer_alloc);
+    m.def("peer_export", &peer_export);
+    m.def("peer_open", &peer_open);
+    m.def("peer_close", &peer_close);
     m.def("strerror", [](int rc) { return std::string(optistate_kf_strerror(rc)); });
     m.def("launch_count", []() { return optistate_kf_launch_count(); });
     m.def("abi_version", []() { return optistate_kf_abi_version(); });
     m.def("desc_size", []() { return (int64_t)optistate_kf_desc_size(); });
     m.attr("SUMMARY_ROWS") = (int)OPTI_KF_SUMMARY_ROWS;
+    m.attr("MAX_PEERS") = (int)OPTI_KF_MAX_PEERS;
 }

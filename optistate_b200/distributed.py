@@ -35,21 +35,31 @@ def gather_columns(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
         raise ValueError(f"local shard has {local.shape[-1]} trajectories, expected {sizes[dist.get_rank(group)]}")
     pad = max(sizes)
     C = local.shape[0]
-    send = local.new_zeros((pad, C))
-    send[: local.shape[-1]] = local.t()  # trajectory-major rows so that the gathered buffer is one contiguous block per rank
-    recv = local.new_empty((world * pad, C))
-    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
-    parts = [recv[r * pad : r * pad + sizes[r]] for r in range(world)]
-    return torch.cat(parts, dim=0).t().contiguous()
+    if pad == local.shape[-1]:
+        send = local.contiguous()
+    else:
+        send = local.new_zeros((C, pad))
+        send[:, : local.shape[-1]] = local
+    recv = local.new_empty((world * C, pad))  # one [C, pad] block per rank
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, C, pad)
+    out = local.new_empty((C, n_total))
+    col = 0
+    for r in range(world):
+        out[:, col : col + sizes[r]] = recv[r, :, : sizes[r]]
+        col += sizes[r]
+    return out
 
 
 def kf_batch_sharded(streams: Dict[str, torch.Tensor], n_total: int, *, Q=None, R=None, x0=None, member_offset: int = 0,
-                     gather: bool = True, group=None, **kw):
+                     gather=True, group=None, **kw):
     """Filters this rank's contiguous block of `n_total` trajectories and (optionally) all-gathers the summaries.
 
     streams: dict with imu, p, dp, contact, f (and optional truth, nominal), replicated on every rank ([T, C, S]).
     Q, R, x0: either shared, or per-trajectory arrays for the LOCAL block ([C, n_local]).
     Trajectory i (global id) reads stream (i + member_offset) % S, so the shard boundary does not change the mapping.
+    gather: True / "nccl" = NCCL all-gather after the kernel; a peer.PeerSummary = the all-gather fused into the filter
+    kernel (NVLink peer stores, see peer.py); False = no gather.
     Returns (KfBatchResult of the local block, gathered summary [52, n_total] or None).
     """
     from .batch import kf_batch
@@ -58,12 +68,21 @@ def kf_batch_sharded(streams: Dict[str, torch.Tensor], n_total: int, *, Q=None, 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     begin, end = shard_range(n_total, world, rank)
     outputs = tuple(kw.pop("outputs", ("summary",)))
-    if gather and "summary" not in outputs:
+    if gather is not False and "summary" not in outputs:
         outputs = outputs + ("summary",)
+    fused = gather if hasattr(gather, "cfg") else None
+    if fused is not None:
+        if fused.n_total != n_total:
+            raise ValueError("PeerSummary was set up for another trajectory count")
+        fused.wait()  # every rank is done with the previous contents of the shared array
+        kw["summary_peers"] = fused
     res = kf_batch(streams["imu"], streams["p"], streams["dp"], streams["contact"], streams["f"], x0=x0, Q=Q, R=R,
                    n_traj=end - begin, stream_offset=begin + member_offset, truth=streams.get("truth"),
                    nominal=streams.get("nominal"), outputs=outputs, **kw)
     gathered: Optional[torch.Tensor] = None
-    if gather:
+    if fused is not None:
+        fused.wait()  # all kernels have finished: every copy is complete
+        gathered = fused.tensor
+    elif gather:
         gathered = gather_columns(res.summary, n_total, group=group)
     return res, gathered

@@ -29,7 +29,8 @@ def test_every_declared_symbol_is_exported(lib):
     syms = declared_symbols()
     assert {"optistate_kf_batch", "optistate_kf_batch_f64", "optistate_kf_batch_f32", "optistate_kf_measure",
             "optistate_kf_resolve_algo", "optistate_kf_workspace_bytes", "optistate_fma_peak", "optistate_kf_launch_count",
-            "optistate_kf_strerror", "optistate_kf_abi_version", "optistate_kf_desc_size"} <= set(syms)
+            "optistate_kf_strerror", "optistate_kf_abi_version", "optistate_kf_desc_size", "optistate_kf_peer_alloc",
+            "optistate_kf_peer_free", "optistate_kf_peer_export", "optistate_kf_peer_open", "optistate_kf_peer_close"} <= set(syms)
     for s in syms:
         assert getattr(lib, s) is not None, s
 
@@ -56,7 +57,8 @@ def _desc_class(lib):
                     + [(n, P) for n in ("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "nis_steps")]
                     + [("ckpt_every", I64)]
                     + [(n, P) for n in ("P_ckpt", "x_final", "P_final", "K_final", "summary", "status", "workspace")]
-                    + [("workspace_bytes", ctypes.c_size_t)])
+                    + [("workspace_bytes", ctypes.c_size_t), ("summary_ld", I64), ("n_summary_peers", I32), ("reserved0", I32),
+                       ("summary_peers", P * 7)])
 
     lib.optistate_kf_desc_size.restype = ctypes.c_size_t
     assert ctypes.sizeof(Desc) == lib.optistate_kf_desc_size()
@@ -111,6 +113,17 @@ def test_descriptor_validation_and_algo_resolution(lib):
     d = _valid_desc(lib)
     d.n_traj = 0  # nothing to do: succeeds without touching the device
     assert lib.optistate_kf_batch(ctypes.byref(d), None) == 0
+    # fused summary all-gather: the row stride must cover the local block, peers must be given
+    d = _valid_desc(lib)
+    d.summary = ctypes.c_void_p(0x1000)
+    d.summary_ld = 3
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == -4
+    d.summary_ld, d.n_summary_peers = 8, 8
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == -4
+    d.n_summary_peers = 1
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == -1  # peer pointer missing
+    d.summary_peers[0] = 0x2000
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == 2
 
 
 def test_workspace_query(lib):
@@ -126,7 +139,7 @@ def test_extension_loads_and_refuses_cpu_tensors():
     from optistate_b200 import _native as nv
 
     ext = nv.ext()
-    assert ext.abi_version() == 1 and ext.launch_count() >= 0
+    assert ext.abi_version() == 2 and ext.MAX_PEERS == 7 and ext.launch_count() >= 0
     cfg = dict(dtype=nv.F64, n_traj=1, n_steps=1, n_streams=1)
     consts = dict(dt=0.01, mass=8.8, inertia0=0.05, inertia1=0.06, inertia2=0.1, gravity=-9.81)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
