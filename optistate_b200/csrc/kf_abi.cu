@@ -146,8 +146,8 @@ bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S,
 
 // returns OPTI_KF_OK, an error, or +1 when the tensor maps could not be built (caller falls back to the direct kernel)
 // Real = double | float | okf::F2 (two FP32 trajectories per thread)
-template <typename Real, bool kSummary>
-int launch_seq_tma(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
+template <typename Real, bool kSummary, bool kSteps>
+int launch_seq_tma_k(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
     constexpr int L = okf::Lanes<Real>::n;
     const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
     okf::TmaMaps maps;
@@ -158,13 +158,20 @@ int launch_seq_tma(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cuda
     if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw);
     if (!ok) return 1;
     const size_t smem = okf::TmaSmem<Real>::total(n_lab, kSummary && sizeof(Real) == 8);
-    auto kern = okf::kf_seq_tma_kernel<Real, kSummary>;
+    auto kern = okf::kf_seq_tma_kernel<Real, kSummary, kSteps>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     const long long per_block = (long long)okf::TMA_THREADS * L;
     const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
     kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p, maps);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return OPTI_KF_OK;
+}
+
+// per-step outputs are compiled out of the kernel when none is wanted (see kf_seq_tma.cuh)
+template <typename Real, bool kSummary>
+int launch_seq_tma(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    const bool steps = p.x_steps || p.x_model_steps || p.p_world_steps || p.z_steps || p.p_trace_steps || p.k_gain_steps || p.nis_steps || p.P_ckpt;
+    return steps ? launch_seq_tma_k<Real, kSummary, true>(p, stream) : launch_seq_tma_k<Real, kSummary, false>(p, stream);
 }
 
 inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }

@@ -109,7 +109,11 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
     }
 }
 
-template <typename Real, bool kSummary>
+// kSteps: some per-step output (x_steps, x_model_steps, p_world_steps, z_steps, p_trace_steps, k_gain_steps, nis_steps,
+// P_ckpt) is wanted.  Without it those blocks are compiled out instead of being jumped over every step: the taken
+// branches across them cost the lone warp of a scheduler ~10 % of its time in instruction-fetch bubbles (ncu:
+// stall_no_inst / stall_branch_resolving at the branch targets of the 35 KB loop body).
+template <typename Real, bool kSummary, bool kSteps>
 __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) ? 3 : 2) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
@@ -209,6 +213,19 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         }
     }
 
+    auto trace_of = [](const Real (&Pm)[NP]) {
+        Real tr = Real(0);
+#pragma unroll
+        for (int c = 0; c < NX; ++c) tr += Pm[tri(c, c)];
+        return tr;
+    };
+    auto gain_trace = [](const Real (&Pm)[NP], const Real *rr) {  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
+        Real g = Real(0);
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) g += div_(Pm[tri(j, sel(j))], rr[j * TMA_THREADS]);
+        return g;
+    };
+
     // rotation of the prior attitude for step 0; inside the loop it is produced one step ahead
     Real Rm[9];
     rot_zyx(x[0], x[1], x[2], Rm);
@@ -217,17 +234,18 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     for (long long t = 0; t < prm.T; ++t) {
         const uint32_t par = (uint32_t)(t & 1);
         const bool more = t + 1 < prm.T;
-        const bool last = !more;
 
         // ---- G0: feet and forces -> mean model --------------------------------------------------------------
         mbar_wait(&bars[0], par);
-        propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc, active ? prm.p_world_steps : nullptr,
-                              (t * 12) * N + i, N);
+        propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc,
+                              (kSteps && active) ? prm.p_world_steps : nullptr, (t * 12) * N + i, N);
         __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
         if (more) issue_g0(maps, t + 1, s_warp, g0w, &bars[0], lane);
-        if (active && prm.x_model_steps) {
+        if constexpr (kSteps) {
+            if (active && prm.x_model_steps) {
 #pragma unroll
-            for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
+                for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
+            }
         }
 
         cov_predict_sym(P, Rm, prm.dt, q, nt);
@@ -235,9 +253,11 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
         mbar_wait(&bars[1], par);
         const Real *z = g1w + lane;
-        if (active && prm.z_steps) {
+        if constexpr (kSteps) {
+            if (active && prm.z_steps) {
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) st_traj(prm.z_steps, (t * NZ + c) * N + i, z[c * 32]);
+                for (int c = 0; c < NZ; ++c) st_traj(prm.z_steps, (t * NZ + c) * N + i, z[c * 32]);
+            }
         }
         Real nis = Real(0), inv, inv_n;
         {
@@ -265,31 +285,27 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         });
 
         ymax = max_(ymax, nis);
-        ptrace = Real(0);
-#pragma unroll
-        for (int c = 0; c < NX; ++c) ptrace += P[tri(c, c)];
-        if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
-            kgain = Real(0);  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
-#pragma unroll
-            for (int j = 0; j < NZ; ++j) kgain += div_(P[tri(j, sel(j))], r[j * nt]);
-        }
 #pragma unroll
         for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
 
-        if (active) {
-            if (prm.x_steps) {
+        if constexpr (kSteps) {
+            ptrace = trace_of(P);
+            if (prm.k_gain_steps != nullptr) kgain = gain_trace(P, r);
+            if (active) {
+                if (prm.x_steps) {
 #pragma unroll
-                for (int c = 0; c < NX; ++c) st_traj(prm.x_steps, (t * NX + c) * N + i, x[c]);
-            }
-            if (prm.p_trace_steps) st_traj(prm.p_trace_steps, t * N + i, ptrace);
-            if (prm.k_gain_steps) st_traj(prm.k_gain_steps, t * N + i, kgain);
-            if (prm.nis_steps) st_traj(prm.nis_steps, t * N + i, nis);
-            if (prm.P_ckpt && prm.ckpt_every > 0 && (t + 1) % prm.ckpt_every == 0) {
-                const long long base = ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
+                    for (int c = 0; c < NX; ++c) st_traj(prm.x_steps, (t * NX + c) * N + i, x[c]);
+                }
+                if (prm.p_trace_steps) st_traj(prm.p_trace_steps, t * N + i, ptrace);
+                if (prm.k_gain_steps) st_traj(prm.k_gain_steps, t * N + i, kgain);
+                if (prm.nis_steps) st_traj(prm.nis_steps, t * N + i, nis);
+                if (prm.P_ckpt && prm.ckpt_every > 0 && (t + 1) % prm.ckpt_every == 0) {
+                    const long long base = ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
 #pragma unroll
-                for (int a = 0; a < NX; ++a)
+                    for (int a = 0; a < NX; ++a)
 #pragma unroll
-                    for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
+                        for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
+                }
             }
         }
 
@@ -339,6 +355,10 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             for (int b = 0; b < NX; ++b) st_traj(prm.P_final, (long long)(a * NX + b) * N + i, P[tri(a, b)]);
     }
     if (kSummary && prm.summary) {
+        if (prm.T > 0) {  // of the last step: the posterior P is still in registers
+            ptrace = trace_of(P);
+            kgain = gain_trace(P, r);
+        }
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
