@@ -41,7 +41,7 @@ FLOPS_ALGORITHMIC = 6800.0  # per trajectory-step, reference ope
 # streams), counted by ncu in the SASS of its time loop (profiles/r1_ncu_bench_kernel_*_hotloop.txt):
 #   FP64: 1135 DFMA + 321 DMUL + 112 DADD;  FP32 (two trajectories per thread): (1051 FFMA2 + 302 FMUL2 + 97 FADD2) x 2 lanes
 #   + 54 FFMA + 30 FMUL + 8 FADD per PAIR of trajectories
-FLOPS_EXECUTED = {"f64": 2 * 1135 + 321 + 112, "f32": (2 * 2 * 1051 + 2 * 302 + 2 * 97 + 2 * 54 + 30 + 8) / 2}
+FLOPS_EXECUTED = {"f64": 2 * 1135 + 321 + 99, "f32": (2 * 2 * 1051 + 2 * 302 + 2 * 85 + 2 * 54 + 30 + 8) / 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the ncu
 # captures summarised in profiles/r1_ncu_bench_kernel_*_metrics.txt; None for any other workload shape
 TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 3.829e9 + 0.433e9, ("f32", 1 << 20, 1000, 1024): 1.422e9 + 0.218e9}

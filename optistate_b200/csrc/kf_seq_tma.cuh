@@ -213,6 +213,29 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         }
     }
 
+    // label tiles of this lane; a label stream that was not given reads the (always valid) feet tile and is ignored
+    const Real *lab_truth = (kSummary && prm.truth) ? g2w + lane : g0w + lane;
+    const Real *lab_nominal = (kSummary && prm.nominal) ? g2w + (prm.truth ? 12 * 32 : 0) + lane : g0w + lane;
+    // labels and running sums are fetched six at a time BEFORE they are used, so the shared-memory latency of one batch
+    // overlaps the arithmetic around it
+    auto accumulate = [&](int acc0, const Real *lab) {
+#pragma unroll
+        for (int c0 = 0; c0 < NX; c0 += 6) {
+            Real lv[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) lv[c] = lab[(c0 + c) * 32];
+            if constexpr (kAccSmem) {
+                AccT av[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) av[c] = acc_s[(acc0 + c0 + c) * nt];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc_s[(acc0 + c0 + c) * nt] = err_acc(av[c], x[c0 + c], lv[c]);
+            } else if constexpr (kSummary) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc_r[acc0 + c0 + c] = err_acc(acc_r[acc0 + c0 + c], x[c0 + c], lv[c]);
+            }
+        }
+    };
     auto trace_of = [](const Real (&Pm)[NP]) {
         Real tr = Real(0);
 #pragma unroll
@@ -252,6 +275,9 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
         mbar_wait(&bars[1], par);
+        if constexpr (kSummary) {
+            if (n_lab) mbar_wait(&bars[2], par);  // G2 (labels, fetched a step ahead like G0 / G1): used inside the last fold
+        }
         const Real *z = g1w + lane;
         if constexpr (kSteps) {
             if (active && prm.z_steps) {
@@ -282,6 +308,13 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
             rot_zyx(x[0], x[1], x[2], Rm);
             any_trunc = may_truncate(Rm);
+            // ... and the running error sums of the summary: straight-line code (no branch on which label streams exist, an
+            // absent one reads a valid dummy tile and is masked at the end), so that its shared-memory round trips are
+            // scheduled underneath the 78 independent FMAs of the rank-1 update instead of stalling the tail of the step
+            if constexpr (kSummary) {
+                accumulate(0, lab_truth);
+                accumulate(12, lab_nominal);
+            }
         });
 
         ymax = max_(ymax, nis);
@@ -309,35 +342,10 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             }
         }
 
-        // ---- G2: label streams -> running error sums -------------------------------------------------------------
         if constexpr (kSummary) {
             acc_add(24, to_acc(nis));
             if (n_lab) {
-                mbar_wait(&bars[2], par);
-                const Real *lab = g2w + lane;
-                // labels and running sums are fetched six at a time BEFORE they are used, so the shared-memory latency of
-                // one batch overlaps the arithmetic of the previous one instead of stalling every single update
-                auto accumulate = [&](int acc0, int lab0) {
-#pragma unroll
-                    for (int c0 = 0; c0 < NX; c0 += 6) {
-                        Real lv[6];
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) lv[c] = lab[(lab0 + c0 + c) * 32];
-                        if constexpr (kAccSmem) {
-                            AccT av[6];
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) av[c] = acc_s[(acc0 + c0 + c) * nt];
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) acc_s[(acc0 + c0 + c) * nt] = err_acc(av[c], x[c0 + c], lv[c]);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) acc_r[acc0 + c0 + c] = err_acc(acc_r[acc0 + c0 + c], x[c0 + c], lv[c]);
-                        }
-                    }
-                };
-                if (prm.truth) accumulate(0, 0);
-                if (prm.nominal) accumulate(12, prm.truth ? 12 : 0);
-                __syncwarp();
+                __syncwarp();  // every lane has consumed this step's labels: refill G2 for step t + 1
                 if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], lane);
             }
         }
@@ -364,8 +372,8 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         for (int c = 0; c < NX; ++c) {
             st_summary(prm, c, i, x[c]);
             st_summary(prm, 12 + c, i, P[tri(c, c)]);
-            st_summary(prm, 24 + c, i, rms_out(acc_get(c), invT, Real()));
-            st_summary(prm, 36 + c, i, rms_out(acc_get(12 + c), invT, Real()));
+            st_summary(prm, 24 + c, i, prm.truth ? rms_out(acc_get(c), invT, Real()) : Real(0));
+            st_summary(prm, 36 + c, i, prm.nominal ? rms_out(acc_get(12 + c), invT, Real()) : Real(0));
         }
         st_summary(prm, 48, i, mean_out(acc_get(24), invT, Real()));
         st_summary(prm, 49, i, ptrace);
