@@ -39,12 +39,12 @@ sys.path.insert(0, ROOT)
 FLOPS_ALGORITHMIC = 6800.0  # per trajectory-step, reference operand order, structural zeros skipped
 # flops the streamed SEQUENTIAL kernel actually executes per trajectory-step in this workload (summary on, two label
 # streams), counted by ncu in the SASS of its time loop (profiles/r1_ncu_bench_kernel_*_hotloop.txt):
-#   FP64: 1135 DFMA + 321 DMUL + 112 DADD;  FP32 (two trajectories per thread): (1051 FFMA2 + 302 FMUL2 + 97 FADD2) x 2 lanes
+#   FP64: 1135 DFMA + 321 DMUL + 99 DADD;  FP32 (two trajectories per thread): (1051 FFMA2 + 302 FMUL2 + 85 FADD2) x 2 lanes
 #   + 54 FFMA + 30 FMUL + 8 FADD per PAIR of trajectories
 FLOPS_EXECUTED = {"f64": 2 * 1135 + 321 + 99, "f32": (2 * 2 * 1051 + 2 * 302 + 2 * 85 + 2 * 54 + 30 + 8) / 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the ncu
 # captures summarised in profiles/r1_ncu_bench_kernel_*_metrics.txt; None for any other workload shape
-TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 3.829e9 + 0.433e9, ("f32", 1 << 20, 1000, 1024): 1.422e9 + 0.218e9}
+TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 2.645e9 + 0.435e9, ("f32", 1 << 20, 1000, 1024): 1.169e9 + 0.214e9}
 # algorithmic bytes of one launch: every base-stream channel read once (p, f, z, two label streams = 58 scalars per
 # stream-step) + 22 noise scalars in and 52 summary scalars out per trajectory
 def algorithmic_bytes(a, esz):
@@ -366,11 +366,14 @@ def run_native(a):
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) * 1e-3
+            best = float("inf")
+            for _ in range(3):
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) * 1e-3)
+            return best
         reps = max(1, 10000 // T)  # the 1,000-step streams repeated in time: the data content does not matter for the rate
         st2 = {k: d[k][:, :, :1024].repeat(reps, 1, 1).contiguous() for k in ("imu", "p", "dp", "contact", "f")}
         t2 = once(lambda: kf_batch(st2["imu"], st2["p"], st2["dp"], st2["contact"], st2["f"], outputs=("x_steps", "p_trace", "k_gain")))
