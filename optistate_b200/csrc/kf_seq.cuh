@@ -115,9 +115,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
 #pragma unroll
         for (int c = 0; c < NX; ++c) ptrace += P[tri(c, c)];
         if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
-            kgain = Real(0);  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
-#pragma unroll
-            for (int j = 0; j < NZ; ++j) kgain += div_(P[tri(j, sel(j))], r[j * nt]);
+            kgain = gain_trace(P, r, nt);
         }
 #pragma unroll
         for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);

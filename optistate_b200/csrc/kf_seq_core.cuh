@@ -135,6 +135,17 @@ __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Rea
     for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
 }
 
+// K_gain of the reference (np.trace of the 12x10 gain): K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j.  The ten
+// reciprocals are the straight-line rcp_ (<= 2 ulp), not IEEE divisions: each division carries a branch to a slow path, and
+// ten of those in a row cost a lone warp ~4,000 cycles per step (measured on the 1,024 x 10 k case with k_gain_steps on).
+template <typename Real>
+__device__ __forceinline__ Real gain_trace(const Real (&P)[NP], const Real *r, int stride) {
+    Real g = Real(0);
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) g = fma_(P[tri(j, sel(j))], rcp_(r[j * stride]), g);
+    return g;
+}
+
 // cheap test whether trunc(R^T) can have a non-zero entry in any lane (then the exact decision is taken per lane)
 template <typename Real>
 __device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {

@@ -242,12 +242,6 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         for (int c = 0; c < NX; ++c) tr += Pm[tri(c, c)];
         return tr;
     };
-    auto gain_trace = [](const Real (&Pm)[NP], const Real *rr) {  // K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j
-        Real g = Real(0);
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) g += div_(Pm[tri(j, sel(j))], rr[j * TMA_THREADS]);
-        return g;
-    };
 
     // rotation of the prior attitude for step 0; inside the loop it is produced one step ahead
     Real Rm[9];
@@ -323,7 +317,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 
         if constexpr (kSteps) {
             ptrace = trace_of(P);
-            if (prm.k_gain_steps != nullptr) kgain = gain_trace(P, r);
+            if (prm.k_gain_steps != nullptr) kgain = gain_trace(P, r, nt);
             if (active) {
                 if (prm.x_steps) {
 #pragma unroll
@@ -365,7 +359,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     if (kSummary && prm.summary) {
         if (prm.T > 0) {  // of the last step: the posterior P is still in registers
             ptrace = trace_of(P);
-            kgain = gain_trace(P, r);
+            kgain = gain_trace(P, r, nt);
         }
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll
