@@ -20,10 +20,8 @@ KF_LIB = os.path.join(LIB_DIR, "liboptistate_kf.so")
 EXT_NAME = "_optistate_torch"
 EXT_LIB = os.path.join(LIB_DIR, EXT_NAME + ".so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--threads", "4",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 
 def _newer(target: str, sources) -> bool:
@@ -41,15 +39,33 @@ def _nvcc() -> str:
 
 
 def build_kf_lib(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(LIB_DIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(ROOT, "include", "optistate_kf.h"))
-    if not force and _newer(KF_LIB, srcs):
-        return KF_LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", KF_LIB, os.path.join(CSRC, "kf_abi.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+    """Compiles every csrc/*.cu to an object (in parallel: the kernel instantiations are spread over several
+    translation units for exactly that reason) and links them into liboptistate_kf.so."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    headers.append(os.path.join(ROOT, "include", "optistate_kf.h"))
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    if not force and _newer(KF_LIB, headers + [os.path.join(CSRC, u) for u in units]):
+        return KF_LIB  # the library alone is enough (the objects do not travel to the GPU box)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = [os.path.join(OBJ_DIR, u[:-3] + ".o") for u in units]
+    todo = [(u, o) for u, o in zip(units, objs) if force or not _newer(o, headers + [os.path.join(CSRC, u)])]
+
+    def compile_one(uo):
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", "-o", uo[1], os.path.join(CSRC, uo[0])]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as pool:
+            list(pool.map(compile_one, todo))
+    stale = [o for o in os.listdir(OBJ_DIR) if os.path.join(OBJ_DIR, o) not in objs]
+    for o in stale:
+        os.remove(os.path.join(OBJ_DIR, o))
+    if todo or stale or not _newer(KF_LIB, objs):
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", KF_LIB, *objs])
     return KF_LIB
 
 

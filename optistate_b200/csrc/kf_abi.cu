@@ -7,9 +7,7 @@
 
 #include "kf_features.cuh"
 #include "kf_identify.cuh"
-#include "kf_joint_coop.cuh"
-#include "kf_seq.cuh"
-#include "kf_seq_tma.cuh"
+#include "kf_launch.cuh"
 
 namespace {
 
@@ -46,8 +44,7 @@ int validate(const OptiKfDesc *d) {
 
 // SEQUENTIAL covers the full recursion with diagonal noise; everything else is JOINT.
 bool sequential_ok(const OptiKfDesc *d) {
-    return is_diag_kind(d->q_kind) && is_diag_kind(d->r_kind) && d->cov_model == OPTI_KF_COV_PREDICT &&
-           d->K_final == nullptr &&
+    return is_diag_kind(d->q_kind) && is_diag_kind(d->r_kind) && d->K_final == nullptr &&
            (d->phases == OPTI_KF_PHASE_ALL || (d->phases == (OPTI_KF_PHASE_PREDICT | OPTI_KF_PHASE_UPDATE) && d->z_in));
 }
 
@@ -112,66 +109,8 @@ bool tma_layout_ok(const OptiKfDesc *d) {
     if (d->n_steps * 12 >= (1LL << 31)) return false;
     if (!aligned16(d->p) || !aligned16(d->f)) return false;
     if (d->summary && ((d->truth && !aligned16(d->truth)) || (d->nominal && !aligned16(d->nominal)))) return false;
+    if (d->cov_model == OPTI_KF_COV_MPC && !aligned16(d->body_ref)) return false;
     return true;
-}
-
-// cuTensorMapEncodeTiled, fetched from the driver through the runtime (no link-time dependency on libcuda)
-using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-    static const EncodeTiledFn fn = [] {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            sym = nullptr;
-        return (EncodeTiledFn)sym;
-    }();
-    return fn;
-}
-
-// [T*C][S] matrix of one per-step input array, fetched in [C][32] boxes (one warp's tile of one step)
-template <typename Real>
-bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S, int box_w) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc || !base) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)(T * C)};
-    const cuuint64_t gstride[1] = {(cuuint64_t)S * sizeof(Real)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)C};
-    const cuuint32_t estride[2] = {1u, 1u};
-    return enc(m, sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride,
-               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// returns OPTI_KF_OK, an error, or +1 when the tensor maps could not be built (caller falls back to the direct kernel)
-// Real = double | float | okf::F2 (two FP32 trajectories per thread)
-template <typename Real, bool kSummary, bool kSteps>
-int launch_seq_tma_k(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
-    constexpr int L = okf::Lanes<Real>::n;
-    const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
-    okf::TmaMaps maps;
-    std::memset(&maps, 0, sizeof maps);
-    const int bw = 32 * L;
-    bool ok = make_map(&maps.p, p.p, p.T, 12, p.S, bw) && make_map(&maps.f, p.f, p.T, 12, p.S, bw) && make_map(&maps.z, p.z_in, p.T, 10, p.S, bw);
-    if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw);
-    if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw);
-    if (!ok) return 1;
-    const size_t smem = okf::TmaSmem<Real>::total(n_lab, kSummary && sizeof(Real) == 8);
-    auto kern = okf::kf_seq_tma_kernel<Real, kSummary, kSteps>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
-    const long long per_block = (long long)okf::TMA_THREADS * L;
-    const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
-    kern<<<blocks, okf::TMA_THREADS, smem, stream>>>(p, maps);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return OPTI_KF_OK;
-}
-
-// per-step outputs are compiled out of the kernel when none is wanted (see kf_seq_tma.cuh)
-template <typename Real, bool kSummary>
-int launch_seq_tma(const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
-    const bool steps = p.x_steps || p.x_model_steps || p.p_world_steps || p.z_steps || p.p_trace_steps || p.k_gain_steps || p.nis_steps || p.P_ckpt;
-    return steps ? launch_seq_tma_k<Real, kSummary, true>(p, stream) : launch_seq_tma_k<Real, kSummary, false>(p, stream);
 }
 
 inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
@@ -199,12 +138,12 @@ template <typename Scalar>
 int launch_streamed(const OptiKfDesc *d, const okf::Params<Scalar> &p, cudaStream_t stream);
 template <>
 int launch_streamed<double>(const OptiKfDesc *d, const okf::Params<double> &p, cudaStream_t stream) {
-    return d->summary ? launch_seq_tma<double, true>(p, stream) : launch_seq_tma<double, false>(p, stream);
+    return d->summary ? okf::launch_seq_tma<double, true>(p, stream) : okf::launch_seq_tma<double, false>(p, stream);
 }
 template <>
 int launch_streamed<float>(const OptiKfDesc *d, const okf::Params<float> &p, cudaStream_t stream) {
-    if (packed_pair_ok(d)) return d->summary ? launch_seq_tma<okf::F2, true>(p, stream) : launch_seq_tma<okf::F2, false>(p, stream);
-    return d->summary ? launch_seq_tma<float, true>(p, stream) : launch_seq_tma<float, false>(p, stream);
+    if (packed_pair_ok(d)) return d->summary ? okf::launch_seq_tma<okf::F2, true>(p, stream) : okf::launch_seq_tma<okf::F2, false>(p, stream);
+    return d->summary ? okf::launch_seq_tma<float, true>(p, stream) : okf::launch_seq_tma<float, false>(p, stream);
 }
 
 template <typename Real>
@@ -235,24 +174,17 @@ int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
         if (streamed) {
             const int rc = launch_streamed<Real>(d, p, stream);
             if (rc < 0) return rc;
-            if (rc == OPTI_KF_OK) return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+            if (rc == OPTI_KF_OK) {
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
+            }
             // tensor maps unavailable: the direct-load kernel below consumes the same (pre-formed) z
         }
-        constexpr int kThreads = 128;
-        const unsigned blocks = (unsigned)((d->n_traj + kThreads - 1) / kThreads);
-        const size_t smem = (size_t)okf::SEQ_NOISE_ROWS * kThreads * sizeof(Real);
-        if (d->summary)
-            okf::kf_seq_kernel<Real, true><<<blocks, kThreads, smem, stream>>>(p);
-        else
-            okf::kf_seq_kernel<Real, false><<<blocks, kThreads, smem, stream>>>(p);
+        const int rc = okf::launch_seq_direct<Real>(p, stream);
+        if (rc < 0) return rc;
     } else {
-        {
-            const size_t smem = okf::jc_smem_bytes<Real>();
-            auto kern = okf::kf_joint_coop_kernel<Real>;
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
-            const unsigned blocks = (unsigned)((d->n_traj + okf::JC_TRAJ - 1) / okf::JC_TRAJ);
-            kern<<<blocks, okf::JC_THREADS, smem, stream>>>(p);
-        }
+        const int rc = okf::launch_joint<Real>(p, stream);
+        if (rc < 0) return rc;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;

@@ -10,7 +10,7 @@ namespace okf {
 
 constexpr int SEQ_NOISE_ROWS = 22;  // shared memory rows per thread: q[12] r[10]
 
-template <typename Real, bool kSummary>
+template <typename Real, bool kSummary, bool kMpc>
 __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Params<Real> prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *noise = reinterpret_cast<Real *>(smem_raw);  // [SEQ_NOISE_ROWS][blockDim.x]
@@ -87,7 +87,18 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
             for (int c = 0; c < NZ; ++c) st_stream(prm.z_steps + (t * NZ + c) * N + i, z[c]);
         }
 
-        cov_predict_sym(P, Rm, prm.dt, q, nt);
+        if constexpr (kMpc) {  // predict_mpc covariance model: R of the transition from the reference body angles
+            Real Rb[9], E[9];
+            rot_zyx(ld_stream(prm.body_ref + (t * 12 + 0) * S + s), ld_stream(prm.body_ref + (t * 12 + 1) * S + s),
+                    ld_stream(prm.body_ref + (t * 12 + 2) * S + s), Rb);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) E[3 * a + k] = exp_minus_one(prm.dt * Rb[3 * k + a]);
+            cov_predict_mpc_sym(P, E, exp_minus_one(prm.dt), q, nt);
+        } else {
+            cov_predict_sym(P, Rm, prm.dt, q, nt);
+        }
 
         Real nis = Real(0), inv, inv_n;
         {

@@ -32,6 +32,7 @@ namespace okf {
 constexpr int TMA_THREADS = 128;
 constexpr int TMA_WARPS = TMA_THREADS / 32;
 constexpr int TMA_CH_G0 = 24, TMA_CH_G1 = 10;
+constexpr int TMA_CH_REF = 3;  // reference body angles of the predict_mpc covariance model (kMpc kernels), part of group G0
 constexpr int TMA_NOISE_ROWS = 22;  // q[12] r[10]
 constexpr int TMA_ACC_ROWS = 25;    // running sums of the summary: 0-11 truth, 12-23 nominal, 24 NIS
 
@@ -60,7 +61,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 
 // tensor maps of the per-step input arrays, each viewed as a [T*C][S] matrix with a [C][32] box
 struct alignas(64) TmaMaps {
-    CUtensorMap p, f, z, lab0, lab1;
+    CUtensorMap p, f, z, lab0, lab1, body_ref;
 };
 
 __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, int col, int row, uint64_t *bar) {
@@ -72,25 +73,26 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, 
 
 template <typename Real>
 struct TmaSmem {
-    // dynamic shared memory: [mbarriers 128 B][per warp: G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32]] x 4 warps
+    // dynamic shared memory: [mbarriers 128 B][per warp: G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] x 4 warps
     //                        [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
-    static __host__ __device__ constexpr size_t warp_rows(int n_lab) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab; }
-    static __host__ __device__ constexpr size_t warp_bytes(int n_lab) { return warp_rows(n_lab) * 32 * sizeof(Real); }
+    static __host__ __device__ constexpr size_t warp_rows(int n_lab, int ref_rows) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab + ref_rows; }
+    static __host__ __device__ constexpr size_t warp_bytes(int n_lab, int ref_rows) { return warp_rows(n_lab, ref_rows) * 32 * sizeof(Real); }
     static __host__ __device__ constexpr size_t off_in() { return 128; }
-    static __host__ __device__ constexpr size_t off_noise(int n_lab) { return off_in() + TMA_WARPS * warp_bytes(n_lab); }
-    static __host__ __device__ constexpr size_t off_acc(int n_lab) { return off_noise(n_lab) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
-    static __host__ __device__ constexpr size_t total(int n_lab, bool acc_in_smem) {
-        return off_acc(n_lab) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * 8 : 0);
+    static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + TMA_WARPS * warp_bytes(n_lab, ref_rows); }
+    static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
+    static __host__ __device__ constexpr size_t total(int n_lab, int ref_rows, bool acc_in_smem) {
+        return off_acc(n_lab, ref_rows) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * 8 : 0);
     }
 };
 
 // One elected lane per warp: arm the group's mbarrier with the byte count, then issue the tile copies of step t.
-template <typename Real>
-__device__ __forceinline__ void issue_g0(const TmaMaps &m, long long t, int s_warp, Real *g0w, uint64_t *bar, int lane) {
+template <bool kMpc, typename Real>
+__device__ __forceinline__ void issue_g0(const TmaMaps &m, long long t, int s_warp, Real *g0w, Real *refw, uint64_t *bar, int lane) {
     if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)(TMA_CH_G0 * 32 * sizeof(Real)));
+        mbar_expect_tx(bar, (uint32_t)((TMA_CH_G0 + (kMpc ? TMA_CH_REF : 0)) * 32 * sizeof(Real)));
         tma_tile_g2s(g0w, &m.p, s_warp, (int)(t * 12), bar);
         tma_tile_g2s(g0w + 12 * 32, &m.f, s_warp, (int)(t * 12), bar);
+        if constexpr (kMpc) tma_tile_g2s(refw, &m.body_ref, s_warp, (int)(t * 12), bar);  // rows 0..2 of the step's 12
     }
 }
 template <typename Real>
@@ -113,7 +115,8 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
 // P_ckpt) is wanted.  Without it those blocks are compiled out instead of being jumped over every step: the taken
 // branches across them cost the lone warp of a scheduler ~10 % of its time in instruction-fetch bubbles (ncu:
 // stall_no_inst / stall_branch_resolving at the branch targets of the 35 KB loop body).
-template <typename Real, bool kSummary, bool kSteps>
+// kMpc: the covariance model of predict_mpc (element-wise exp transition, cov_predict_mpc_sym) instead of predict's.
+template <typename Real, bool kSummary, bool kSteps, bool kMpc>
 __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) ? 3 : 2) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
@@ -148,10 +151,12 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     const int n_lab = kSummary ? (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0) : 0;
 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + 3 * warp;  // warp-private: full[G0], full[G1], full[G2]
-    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in() + warp * TmaSmem<Real>::warp_bytes(n_lab));
+    constexpr int kRefRows = kMpc ? TMA_CH_REF : 0;
+    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in() + warp * TmaSmem<Real>::warp_bytes(n_lab, kRefRows));
     Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // this warp's [C][32] tiles (of Real)
-    Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab));
-    AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + TmaSmem<Real>::off_acc(n_lab)) + tid;
+    Real *refw = g2w + 12 * n_lab * 32;                              // reference body angles (kMpc), fetched with G0
+    Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab, kRefRows));
+    AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + TmaSmem<Real>::off_acc(n_lab, kRefRows)) + tid;
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     }
     __syncwarp();
     if (prm.T > 0) {
-        issue_g0(maps, 0, s_warp, g0w, &bars[0], lane);
+        issue_g0<kMpc>(maps, 0, s_warp, g0w, refw, &bars[0], lane);
         issue_g1(maps, 0, s_warp, g1w, &bars[1], lane);
         if (n_lab) issue_g2(maps, 0, s_warp, n_lab, g2w, &bars[2], lane);
     }
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         return tr;
     };
 
+    const Real e1_mpc = kMpc ? exp_minus_one(Real(prm.dt)) : Real(0);
     // rotation of the prior attitude for step 0; inside the loop it is produced one step ahead
     Real Rm[9];
     rot_zyx(x[0], x[1], x[2], Rm);
@@ -256,8 +262,17 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         mbar_wait(&bars[0], par);
         propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc,
                               (kSteps && active) ? prm.p_world_steps : nullptr, (t * 12) * N + i, N);
+        Real E[kMpc ? 9 : 1];  // D[a][6 + k] = exp(dt Rb^T[a][k]) - 1 of the predict_mpc transition (kalman_filter.py:153-157)
+        if constexpr (kMpc) {
+            Real Rb[9];
+            rot_zyx(refw[lane], refw[32 + lane], refw[64 + lane], Rb);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) E[3 * a + k] = exp_minus_one(Real(prm.dt) * Rb[3 * k + a]);
+        }
         __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
-        if (more) issue_g0(maps, t + 1, s_warp, g0w, &bars[0], lane);
+        if (more) issue_g0<kMpc>(maps, t + 1, s_warp, g0w, refw, &bars[0], lane);
         if constexpr (kSteps) {
             if (active && prm.x_model_steps) {
 #pragma unroll
@@ -265,7 +280,8 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             }
         }
 
-        cov_predict_sym(P, Rm, prm.dt, q, nt);
+        if constexpr (kMpc) cov_predict_mpc_sym(P, E, e1_mpc, q, nt);
+        else cov_predict_sym(P, Rm, prm.dt, q, nt);
 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
         mbar_wait(&bars[1], par);

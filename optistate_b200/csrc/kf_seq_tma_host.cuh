@@ -1,0 +1,75 @@
+// Host side of the streamed SEQUENTIAL kernel: tensor maps of the per-step input arrays and the launch.  Included by the
+// kf_seq_tma_*.cu translation units, each of which instantiates launch_seq_tma for one (Real, kSummary) pair.
+#pragma once
+
+#include <cuda.h>
+
+#include <cstring>
+
+#include "kf_launch.cuh"
+#include "kf_seq_tma.cuh"
+
+namespace okf {
+
+// cuTensorMapEncodeTiled, fetched from the driver through the runtime (no link-time dependency on libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+    static const EncodeTiledFn fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return (EncodeTiledFn)sym;
+    }();
+    return fn;
+}
+
+// [T*C][S] matrix of one per-step input array, fetched in [rows][box_w] boxes (one warp's tile of one step; rows = the
+// leading channels of the C that are wanted)
+template <typename Real>
+bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S, int box_w, int rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || !base) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)S, (cuuint64_t)(T * C)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)S * sizeof(Real)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)rows};
+    const cuuint32_t estride[2] = {1u, 1u};
+    return enc(m, sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride,
+               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename Real, bool kSummary, bool kSteps, bool kMpc>
+int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    constexpr int L = Lanes<Real>::n;
+    const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
+    TmaMaps maps;
+    std::memset(&maps, 0, sizeof maps);
+    const int bw = 32 * L;
+    bool ok = make_map(&maps.p, p.p, p.T, 12, p.S, bw, 12) && make_map(&maps.f, p.f, p.T, 12, p.S, bw, 12) &&
+              make_map(&maps.z, p.z_in, p.T, 10, p.S, bw, 10);
+    if (ok && kMpc) ok = make_map(&maps.body_ref, p.body_ref, p.T, 12, p.S, bw, 3);
+    if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw, 12);
+    if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw, 12);
+    if (!ok) return 1;
+    const size_t smem = TmaSmem<Real>::total(n_lab, kMpc ? TMA_CH_REF : 0, kSummary && sizeof(Real) == 8);
+    auto kern = kf_seq_tma_kernel<Real, kSummary, kSteps, kMpc>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
+    const long long per_block = (long long)TMA_THREADS * L;
+    const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
+    kern<<<blocks, TMA_THREADS, smem, stream>>>(p, maps);
+    return OPTI_KF_OK;
+}
+
+// per-step outputs and the predict_mpc covariance model are compile-time variants of the kernel (see kf_seq_tma.cuh)
+template <typename Real, bool kSummary>
+int launch_seq_tma(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    const bool steps = p.x_steps || p.x_model_steps || p.p_world_steps || p.z_steps || p.p_trace_steps || p.k_gain_steps || p.nis_steps || p.P_ckpt;
+    const bool mpc = p.cov_model == OPTI_KF_COV_MPC;
+    if (mpc) return steps ? launch_seq_tma_k<Real, kSummary, true, true>(p, stream) : launch_seq_tma_k<Real, kSummary, false, true>(p, stream);
+    return steps ? launch_seq_tma_k<Real, kSummary, true, false>(p, stream) : launch_seq_tma_k<Real, kSummary, false, false>(p, stream);
+}
+
+}  // namespace okf

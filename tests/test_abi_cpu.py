@@ -92,7 +92,9 @@ def test_descriptor_validation_and_algo_resolution(lib):
     d = _valid_desc(lib)
     d.cov_model = 1
     d.body_ref = ctypes.c_void_p(0x1000)
-    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == 1  # predict_mpc covariance -> JOINT
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == 2  # predict_mpc covariance with diagonal noise -> SEQUENTIAL too
+    d.body_ref = None
+    assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == -1  # ... but it needs the reference body angles
     d = _valid_desc(lib)
     d.K_final = ctypes.c_void_p(0x1000)
     assert lib.optistate_kf_resolve_algo(ctypes.byref(d)) == 1  # the gain matrix only exists in the joint form

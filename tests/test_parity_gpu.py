@@ -87,9 +87,37 @@ def test_fp64_joint_emits_gain_matrix():
 def test_next_row_mpc_covariance_model():
     """predict_mpc's element-wise exp transition.  cond(S) ~ 6e6 there, so the reference's own
     P is only defined to ~1e-9 of max|P| (see tests/test_oracle.py); states stay within the north-star bound."""
-    res = run_case("next_mpc_cov_seed5", "auto")
+    res = run_case("next_mpc_cov_seed5", "joint")
     assert res.algo == "joint"
     compare_golden("next_mpc_cov_seed5", res, parity.FP64_TOL, 5e-8, 5e-8)
+
+
+def test_next_row_mpc_covariance_model_sequential():
+    """The same model on the throughput path: F_d = exp(dt F) element-wise = 1 1^T + sparse (cov_predict_mpc_sym) followed by
+    the scalar updates.  A NumPy prototype of this formulation matched the reference golden to 8e-11 (states) / 1e-11 (P);
+    the bounds are the ones of the joint form above."""
+    res = run_case("next_mpc_cov_seed5", "auto")
+    assert res.algo == "sequential"  # diagonal noise, symmetric P0: AUTO takes the streamed kernel
+    compare_golden("next_mpc_cov_seed5", res, parity.FP64_TOL, 5e-8, 5e-8)
+    # the direct-load kernel (arbitrary stream gather) runs the same arithmetic
+    direct = run_case("next_mpc_cov_seed5", "sequential", stream_index=torch.zeros(1, dtype=torch.int32))
+    assert torch.allclose(direct.x_steps, res.x_steps, rtol=0, atol=1e-12) and torch.allclose(direct.P_final, res.P_final, rtol=1e-10, atol=1e-12)
+    # 64 copies through the packed-tile TMA path == the single stream
+    stream, ckw, _ = cases.build("next_mpc_cov_seed5")
+    s = cases.stack_stream(stream)
+    rep = {k: torch.from_numpy(np.repeat(v, 64, axis=2)).cuda() for k, v in s.items()}
+    kw = dict(x0=ckw["x0"], P0=ckw["P0"], R=ckw["R"], cov_model="mpc", body_ref=rep["body_ref"], outputs=("x_steps", "summary"))
+    f64 = kf_batch(rep["imu"], rep["p"], rep["dp"], rep["contact"], rep["f"], Q=ckw["Q"], dtype=torch.float64, **kw)
+    assert f64.algo == "sequential" and torch.equal(f64.x_steps[:, :, 5], res.x_steps[:, :, 0])
+    # FP32 (packed pair kernel) against FP64.  With the reference's Q the model is too ill-conditioned for FP32 (cond(S) ~ 6e6
+    # against eps 6e-8), so the comparison runs with a small process noise (cond(S) ~ 1)
+    q_small = np.full(12, 1e-6)
+    kw["P0"] = np.diag(q_small)
+    a = kf_batch(rep["imu"], rep["p"], rep["dp"], rep["contact"], rep["f"], Q=q_small, dtype=torch.float64, **kw)
+    b = kf_batch(rep["imu"], rep["p"], rep["dp"], rep["contact"], rep["f"], Q=q_small, dtype=torch.float32, **kw)
+    assert a.algo == b.algo == "sequential" and int(b.status.max()) == 0
+    scale = a.x_steps.abs().amax(dim=(0, 2)).clamp_min(1e-3)
+    assert ((b.x_steps.double() - a.x_steps).abs().amax(dim=(0, 2)) / scale).max() < 5e-4
 
 
 @pytest.mark.parametrize("name", ["default_seed11_10k", "stress_qrpkl_seed3_10k", "cfg1_default_seed0"])

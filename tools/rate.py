@@ -22,6 +22,9 @@ for spec in sys.argv[1:]:
     n = N if out != "x_steps" else min(N, 1 << 18)
     kw = dict(Q=torch.from_numpy(q64[:, :n].copy()).to("cuda", dt), R=torch.from_numpy(r64[:, :n].copy()).to("cuda", dt),
               q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, n_traj=n, dtype=dt, outputs=(out,))
+    if out == "mpc":  # predict_mpc covariance model, summary output
+        out = "summary"
+        kw.update(outputs=("summary",), cov_model="mpc", body_ref=dev["truth"])
     if out == "summary":
         kw.update(truth=dev["truth"], nominal=dev["truth"] * 0.5)
     best = 1e9
