@@ -61,7 +61,7 @@ enum { OPTI_KF_ALGO_AUTO = 0, OPTI_KF_ALGO_JOINT = 1, OPTI_KF_ALGO_SEQUENTIAL = 
 
 /* cov_model: 0 = predict():      F_d = I + dt F               (kalman_filter.py:125-135)
  *            1 = predict_mpc():  F_d = exp(dt F) element-wise, R from body_ref angles (kalman_filter.py:153-158);
- *                JOINT only, needs `body_ref`.                                                                */
+ *                needs `body_ref`; both algos (SEQUENTIAL uses F_d = 1 1^T + a 12-entry sparse matrix).        */
 enum { OPTI_KF_COV_PREDICT = 0, OPTI_KF_COV_MPC = 1 };
 
 /* phases: which parts of a step run (all three for the batched recursion) */
