@@ -218,6 +218,32 @@ typedef struct OptiKfIdentifyDesc {
 size_t optistate_kf_identify_scratch_bytes(int dtype, int64_t n_traj, int64_t n_steps);
 int optistate_kf_identify_noise(const OptiKfIdentifyDesc *desc, void *cuda_stream);
 
+/* ---- next row after those: the convex force MPC that predict_mpc solves for its forces (misc/force_controller.py:15-225,
+ * set up by kalman_filter.py:64-77,140-152), batched.  One strictly convex QP per problem: 5 stages x 4 legs x 3 force
+ * components; swing legs (contact == 0) carry no force, stance legs (contact == 1) satisfy fz <= fz_max, |fx| <= mu fz,
+ * |fy| <= mu fz.  The reference solves it with CasADi + qpOASES, which are not available offline and no reference test pins
+ * a force vector: parity is anchored on the uniqueness of the minimiser (tests check KKT optimality and an independent
+ * active-set solve).  FP64 only. ---- */
+#define OPTI_KF_MPC_HORIZON 5
+enum { OPTI_KF_MPC_ST_IPM_LIMIT = 1,  /* interior-point phase stopped on its iteration cap or a pivot breakdown       */
+       OPTI_KF_MPC_ST_UNPOLISHED = 2  /* active-set polish did not settle: the forces are the interior-point iterate
+                                         (~1e-6 relative) instead of the exact vertex solution                         */ };
+typedef struct OptiKfMpcDesc {
+    uint32_t struct_size, abi_version;
+    int32_t dtype, reserved;       /* OPTI_KF_F64 */
+    int64_t n_problems;
+    const void *x;                 /* [12][N] current state (column 0 of body_mpc, kalman_filter.py:143)              */
+    const void *body_ref;          /* [5][12][N] reference states of the horizon (columns 1..5 of body_mpc)           */
+    const void *p;                 /* [12][N] body-frame feet, held over the horizon (kalman_filter.py:141-142)       */
+    const void *contact;           /* [4][N] 0 / 1 flags stored as dtype, held over the horizon (kalman_filter.py:145-146) */
+    void *forces;                  /* [5][12][N] optimal forces; stage 0 is what predict_mpc applies (kalman_filter.py:161) */
+    uint32_t *status;              /* [N] optional: OPTI_KF_MPC_ST_* | interior-point iterations << 8                  */
+    double dt, mass, inertia[3], gravity;
+    double mu, fz_max;             /* 0.6, 150 (force_controller.py:149-151)                                          */
+    double w_state[12], w_force;   /* diag Q = P (kalman_filter.py:64,70) and the R value (:66)                        */
+} OptiKfMpcDesc;
+int optistate_kf_mpc_forces(const OptiKfMpcDesc *desc, void *cuda_stream);
+
 /* Runs the filter; dtype taken from the descriptor. */
 int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);
 /* Same, asserting the scalar type (the two names a binding would import). */

@@ -20,6 +20,10 @@ def __getattr__(name):
         from .kalman_filter import Kalman_Filter
 
         return Kalman_Filter
+    if name == "mpc_forces":
+        from .mpc import mpc_forces
+
+        return mpc_forces
     if name in ("shard_range", "kf_batch_sharded", "gather_summaries"):
         from . import distributed
 

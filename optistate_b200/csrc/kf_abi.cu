@@ -8,6 +8,7 @@
 #include "kf_features.cuh"
 #include "kf_identify.cuh"
 #include "kf_launch.cuh"
+#include "kf_mpc_params.cuh"
 
 namespace {
 
@@ -457,6 +458,33 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *d, void *cuda_stream) 
     cudaGetLastError();
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     return d->dtype == OPTI_KF_F64 ? identify_noise<double>(d, stream) : identify_noise<float>(d, stream);
+}
+
+int optistate_kf_mpc_forces(const OptiKfMpcDesc *d, void *cuda_stream) {
+    if (!d) return OPTI_KF_E_NULL;
+    if (d->struct_size != sizeof(OptiKfMpcDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
+    if (d->dtype != OPTI_KF_F64) return OPTI_KF_E_DTYPE;  // cond(H) ~ 1e5: the QP is solved in double only
+    if (d->n_problems < 0) return OPTI_KF_E_SHAPE;
+    if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0) || !(d->mu > 0) ||
+        !(d->fz_max > 0) || !(d->w_force > 0))
+        return OPTI_KF_E_SHAPE;
+    for (int k = 0; k < 12; ++k)
+        if (!(d->w_state[k] >= 0)) return OPTI_KF_E_SHAPE;
+    if (d->n_problems == 0) return OPTI_KF_OK;
+    if (!d->x || !d->body_ref || !d->p || !d->contact || !d->forces) return OPTI_KF_E_NULL;
+    okf::MpcParams p;
+    std::memset(&p, 0, sizeof p);
+    p.N = d->n_problems;
+    p.x = (const double *)d->x; p.body_ref = (const double *)d->body_ref; p.p = (const double *)d->p;
+    p.contact = (const double *)d->contact; p.forces = (double *)d->forces; p.status = d->status;
+    p.dt = d->dt; p.inv_mass = 1.0 / d->mass; p.gravity = d->gravity; p.mu = d->mu; p.fz_max = d->fz_max; p.w_force = d->w_force;
+    for (int k = 0; k < 3; ++k) p.inv_inertia[k] = 1.0 / d->inertia[k];
+    for (int k = 0; k < 12; ++k) p.w_state[k] = d->w_state[k];
+    cudaGetLastError();
+    const int rc = okf::launch_mpc(p, (cudaStream_t)cuda_stream);
+    if (rc < 0) return rc;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 
 // ---- peer memory for the fused summary all-gather (cudaIpc: one process per GPU on one box) ----

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "kf_common.cuh"
+#include "kf_mpc_params.cuh"
 
 namespace okf {
 
@@ -21,5 +22,8 @@ int launch_seq_direct(const Params<Real> &p, cudaStream_t stream);
 // JOINT kernel, four lanes per trajectory (kf_joint_coop.cuh).
 template <typename Real>
 int launch_joint(const Params<Real> &p, cudaStream_t stream);
+
+// Batched convex force MPC, one warp per problem (kf_mpc.cuh).
+int launch_mpc(const MpcParams &p, cudaStream_t stream);
 
 }  // namespace okf

@@ -1,0 +1,16 @@
+// Kernel parameters of the batched force MPC (kf_mpc.cuh); separate so that kf_abi.cu can fill them without seeing the kernel.
+#pragma once
+
+#include <stdint.h>
+
+namespace okf {
+
+struct MpcParams {
+    long long N;
+    const double *x, *body_ref, *p, *contact;  // [12][N], [NH*12][N], [12][N], [4][N]
+    double *forces;                             // [NH*12][N]
+    uint32_t *status;                           // [N] optional
+    double dt, inv_mass, inv_inertia[3], gravity, mu, fz_max, w_state[12], w_force;
+};
+
+}  // namespace okf

@@ -8,6 +8,7 @@
 #include <map>
 #include <optional>
 #include <string>
+#include <vector>
 
 #include "../../include/optistate_kf.h"
 
@@ -324,6 +325,37 @@ int kf_identify_noise(int64_t dtype, int64_t n_traj, int64_t n_steps, int64_t n_
     return optistate_kf_identify_noise(&d, at::cuda::getCurrentCUDAStream().stream());
 }
 
+// Convex force MPC: x [12][N], body_ref [5][12][N], p [12][N], contact [4][N] -> forces [5][12][N], status [N]
+int kf_mpc_forces(int64_t n, const std::map<std::string, double> &consts, const std::vector<double> &w_state, const TensorMap &tensors) {
+    OptiKfMpcDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = OPTI_KF_F64;
+    d.n_problems = n;
+    auto x = tensors.find("x");
+    TORCH_CHECK(x != tensors.end() && x->second.is_cuda(), "optistate_b200: 'x' must be a CUDA tensor (there is no CPU path)");
+    TORCH_CHECK(w_state.size() == 12, "optistate_b200: w_state needs 12 entries");
+    const Checker ck{at::kDouble, x->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    d.x = ck.get(tensors, "x", 12 * n, true);
+    d.body_ref = ck.get(tensors, "body_ref", OPTI_KF_MPC_HORIZON * 12 * n, true);
+    d.p = ck.get(tensors, "p", 12 * n, true);
+    d.contact = ck.get(tensors, "contact", 4 * n, true);
+    d.forces = const_cast<void *>(ck.get(tensors, "forces", OPTI_KF_MPC_HORIZON * 12 * n, true));
+    auto is = tensors.find("status");
+    if (is != tensors.end()) {
+        const at::Tensor &t = is->second;
+        TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == n, "optistate_b200: bad 'status'");
+        d.status = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+    }
+    d.dt = consts.at("dt"); d.mass = consts.at("mass"); d.gravity = consts.at("gravity");
+    d.inertia[0] = consts.at("inertia0"); d.inertia[1] = consts.at("inertia1"); d.inertia[2] = consts.at("inertia2");
+    d.mu = consts.at("mu"); d.fz_max = consts.at("fz_max"); d.w_force = consts.at("w_force");
+    for (int k = 0; k < 12; ++k) d.w_state[k] = w_state[k];
+    return optistate_kf_mpc_forces(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
 // ---- peer memory (fused summary all-gather) ----
 at::Tensor peer_alloc(int64_t nbytes, int64_t device_index) {
     TORCH_CHECK(nbytes > 0, "optistate_b200: peer_alloc needs a positive size");
@@ -378,6 +410,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_features", &kf_features);
     m.def("kf_minmax", &kf_minmax);
     m.def("kf_windows", &kf_windows);
+    m.def("kf_mpc_forces", &kf_mpc_forces);
     m.def("peer_alloc", &peer_alloc);
     m.def("peer_export", &peer_export);
     m.def("peer_open", &peer_open);

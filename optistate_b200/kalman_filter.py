@@ -14,8 +14,9 @@ For many trajectories or many steps use `optistate_b200.kf_batch`, which runs th
 Errors follow the reference: `numpy.linalg.LinAlgError` when S is not invertible (kalman_filter.py:168) and
 `ValueError` when no foot is in stance (kalman_filter.py:97-103).
 
-The MPC that produces the forces inside `predict_mpc` (CasADi + qpOASES, force_controller.py:15-225) is out of
-scope; `estimate_state_mpc` / `predict_mpc` therefore take the forces from an injectable `force_provider`.
+The forces inside `predict_mpc` come from the reference's convex MPC (CasADi + qpOASES, force_controller.py:15-225).  Here
+they are solved for on the device by optistate_b200.mpc.mpc_forces (same QP, interior point + active-set polish; parity
+with qpOASES unpinned, see there), unless forces are passed explicitly (`f=`) or an injectable `force_provider` is set.
 """
 from __future__ import annotations
 
@@ -157,11 +158,20 @@ class Kalman_Filter:
         """kalman_filter.py:140-162 with the QP replaced by `force_provider` (or an explicit f):
         covariance by F_d = exp(dt F) element-wise with R from body_ref, mean by next_state with R from x."""
         if f is None:
-            if self.force_provider is None:
-                raise NotImplementedError(
-                    "predict_mpc needs ground-reaction forces: pass f=... or construct Kalman_Filter(force_provider=fn); "
-                    "the CasADi/qpOASES MPC of the reference (force_controller.py:15-225) is out of scope")
-            f = self.force_provider(np.asarray(p), np.asarray(body_ref), np.asarray(cur_contact), np.asarray(self.x))
+            if self.force_provider is not None:
+                f = self.force_provider(np.asarray(p), np.asarray(body_ref), np.asarray(cur_contact), np.asarray(self.x))
+            else:  # kalman_filter.py:141-152: body_mpc = [x | body_ref], feet and contact held over the horizon
+                from .mpc import HORIZON, mpc_forces
+
+                self._dev()  # fails loudly without a GPU: there is no CPU solver
+                ref = np.asarray(body_ref, float)
+                ref = ref if ref.ndim == 2 and ref.shape == (12, HORIZON) else np.repeat(ref.reshape(12, 1), HORIZON, axis=1)
+                forces, st = mpc_forces(np.asarray(self.x, float).reshape(12, 1), ref.T.reshape(HORIZON, 12, 1),
+                                        np.asarray(p, float).reshape(12, 1), np.asarray(cur_contact, float).reshape(4, 1),
+                                        dt=float(self.dt), mass=float(self.m), inertia=np.diag(np.asarray(self.inertia_rot, float)),
+                                        gravity=float(np.asarray(self.g, float).reshape(12)[11]), device=self._dev())
+                self.mpc_status = int(st[0])
+                f = forces[:, :, 0].cpu().numpy().T  # (12, horizon) like sol.value(controls), kalman_filter.py:152
         f = np.asarray(f, float)
         self.f = f if f.ndim == 2 and f.shape[1] > 1 else f.reshape(12, 1)
         f0 = self.f[:, 0].reshape(12)

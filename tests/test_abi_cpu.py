@@ -187,5 +187,6 @@ def test_drop_in_class_surface_matches_reference_attributes():
     assert kf.z.reshape(-1).tolist() == [0, 1, 2, 10, 3, 4, 5, 11, 12, 13]
     R = kf.rotation_matrix_body_world(0.1, -0.2, 0.3)
     assert np.allclose(R @ R.T, np.eye(3), atol=1e-15)
-    with pytest.raises(NotImplementedError):
-        kf.predict_mpc(np.zeros((12, 1)), np.zeros((12, 1)), np.ones((4, 1)))
+    if not torch.cuda.is_available():  # without explicit forces predict_mpc solves the MPC on the device: no CPU solver
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            kf.predict_mpc(np.zeros((12, 1)), np.zeros((12, 1)), np.ones((4, 1)))

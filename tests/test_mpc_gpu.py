@@ -1,0 +1,74 @@
+"""GPU tests of SURVEY 8(f) row 3: the batched force MPC (csrc/kf_mpc.cuh, one warp per QP) against the oracle's
+independent active-set solve and a solver-independent KKT certificate.  Parity with qpOASES is unpinned (see
+oracle/mpc_numpy.py); the QP is strictly convex, so agreement with any exact solver is agreement with the minimiser."""
+import numpy as np
+import pytest
+import torch
+
+from optistate_b200 import Kalman_Filter
+from optistate_b200.mpc import ST_UNPOLISHED, mpc_forces
+from oracle import mpc_numpy as mpc
+from tests import mpc_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_forces_are_the_minimiser_for_all_contact_patterns_and_saturations():
+    n = 256
+    x, ref, p, c = mpc_cases.batch(n, seed=0)
+    forces, status = mpc_forces(x, ref, p, c)
+    torch.cuda.synchronize()
+    F, st = forces.cpu().numpy(), status.cpu().numpy()
+    assert F.shape == (5, 12, n)
+    assert not (st & ST_UNPOLISHED).any(), np.where(st & ST_UNPOLISHED)[0]
+    worst = 0.0
+    for k in range(n):
+        H, g, _ = mpc.build_qp(x[:, k], ref[:, :, k].T, p[:, k])
+        A, b, pinned = mpc.constraints(c[:, k])
+        u = F[:, :, k].reshape(-1)
+        viol, stat = mpc.kkt_certificate(u, H, g, A, b, pinned)
+        assert viol < 1e-7 and stat < 1e-8, (k, c[:, k], viol, stat)            # feasible to 1e-7 N, stationary to 1e-8 |g|
+        want = mpc.solve_ldp(H, g, A, b, pinned)
+        err = np.abs(u - want).max() / max(1.0, np.abs(want).max())
+        worst = max(worst, err)
+        assert err < 1e-8, (k, c[:, k], err)
+        assert np.all(u[pinned] == 0.0)
+    print("worst |u - u_oracle| / max|u|:", worst, " interior-point iterations max:", int((st >> 8).max()))
+    # saturation really occurs in the batch: friction faces and the fz cap
+    assert (np.abs(F[:, 2::3, :] - 150.0) < 1e-6).any() and (np.abs(np.abs(F[:, 0::3, :]) - 0.6 * F[:, 2::3, :]) < 1e-7)[F[:, 2::3, :] > 1].any()
+
+
+def test_all_swing_and_unconstrained_legs():
+    x, ref, p, c = mpc_cases.batch(16, seed=5)
+    c[:] = 0.0
+    forces, status = mpc_forces(x, ref, p, c)
+    assert torch.count_nonzero(forces) == 0 and not (status & 3).any()
+    # a contact value that is neither 0 nor 1 leaves the leg unconstrained (the reference's if_else selects neither set)
+    c[:] = 0.5
+    forces, status = mpc_forces(x, ref, p, c)
+    F = forces.cpu().numpy()
+    for k in range(4):
+        H, g, _ = mpc.build_qp(x[:, k], ref[:, :, k].T, p[:, k])
+        want = np.linalg.solve(H, -g)
+        assert np.abs(F[:, :, k].reshape(-1) - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+
+
+def test_estimate_state_mpc_solves_for_its_forces_on_the_device():
+    """The drop-in class without a force provider: predict_mpc solves the reference's QP (kalman_filter.py:147-152)."""
+    rng = np.random.default_rng(2)
+    x, ref, p = mpc_cases.problem(rng, lateral=0.5)
+    contact = np.array([1.0, 0.0, 0.0, 1.0]).reshape(4, 1)
+    kf = Kalman_Filter()
+    kf.x = x.reshape(12, 1).copy()
+    imu = np.concatenate([x[0:3], x[6:9]]).reshape(6, 1)
+    dp = 0.05 * rng.standard_normal((12, 1))
+    p_in = p.reshape(12, 1).copy()
+    kf.estimate_state_mpc(imu, p_in, dp, ref, contact)
+    want = mpc.solve(x, ref, p, contact)            # (12, 5)
+    assert kf.f.shape == (12, 5)
+    assert np.abs(kf.f - want).max() < 1e-8 * np.abs(want).max()
+    # same step with the oracle's forces supplied explicitly gives the same state
+    kf2 = Kalman_Filter()
+    kf2.x = x.reshape(12, 1).copy()
+    kf2.estimate_state_mpc(imu, p.reshape(12, 1).copy(), dp, ref, contact, f=want)
+    assert np.abs(kf.x - kf2.x).max() < 1e-10
