@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     // ---- condensed QP: H = 2 sum_i Su_i^T W Su_i + 2 R,  g = 2 sum_i Su_i^T W (sc_i - ref_i) ----------------------
     for (int e = lane; e < MPC_TRI; e += 32) H[e] = 0.0;
     for (int e = lane; e < 12 * MPC_N; e += 32) Su[e] = 0.0;
+    __syncwarp();  // the diagonal entries below were zeroed by other lanes
     for (int e = lane; e < MPC_N; e += 32) { g[e] = 0.0; H[tri_idx(e, e)] = 2.0 * prm.w_force; }
     double sc[12];  // free response of the state (replicated in every lane)
 #pragma unroll
@@ -176,13 +177,9 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     for (int k = 0; k < 12; ++k) pf[k] = prm.p[k * N + prob];
     __syncwarp();
     for (int i = 0; i < MPC_NH; ++i) {
-        double th[3];
+        double th[3];  // linearisation angles: body_mpc[0:3, i] = the current state for stage 0, body_ref[:, i - 1] after
 #pragma unroll
-        for (int k = 0; k < 3; ++k) th[k] = i == 0 ? sc[k] : prm.body_ref[((i - 1) * 12 + k) * N + prob];
-        if (i == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) th[k] = prm.x[k * N + prob];
-        }
+        for (int k = 0; k < 3; ++k) th[k] = i == 0 ? prm.x[k * N + prob] : prm.body_ref[((i - 1) * 12 + k) * N + prob];
         double R[9];
         rot_zyx(th[0], th[1], th[2], R);
         // Su <- (I + dt A) Su: rows 0..2 += dt R^T rows 6..8, rows 3..5 += dt rows 9..11 (rows 6..11 unchanged)

@@ -50,3 +50,37 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
                                             dict(x=x_t, body_ref=b_t, p=p_t, contact=c_t, forces=forces, status=status))),
                  "optistate_kf_mpc_forces")
     return forces, status
+
+
+def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=None, R=None, **kw):
+    """The reference's closed loop `KF.estimate_state_mpc(imu, p, dp, body_ref, contact)` (kalman_filter.py:176-182) for N
+    trajectories over T steps, everything on the device: at every step the force MPC is solved for each trajectory from
+    its CURRENT state estimate, then one filter step runs with those forces and the predict_mpc covariance model.
+
+    imu [T,6,N], p [T,12,N], dp [T,12,N], contact [T,4,N], body_ref [T,5,12,N] (horizon reference of each step; the
+    filter's transition uses its first column, as the class does).  Returns (x_steps [T,12,N], forces [T,12,N] - the
+    applied stage-0 forces -, mpc_status [T,N], filter status [N]).
+    """
+    from .batch import _as_device, kf_batch
+
+    nv.require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device())
+    imu, p, dp, contact, body_ref = (_as_device(a, torch.float64, device) for a in (imu, p, dp, contact, body_ref))
+    T, N = imu.shape[0], imu.shape[2]
+    x = _as_device(INITIAL_PARAMS.STARTING_STATE.reshape(12) if x0 is None else x0, torch.float64, device)
+    x = x.reshape(12, 1).repeat(1, N) if x.numel() == 12 else x.reshape(12, N).clone()
+    Pm = None if P0 is None else _as_device(P0, torch.float64, device)
+    xs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
+    fs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
+    mst = torch.empty((T, N), dtype=torch.int32, device=device)
+    fst = torch.zeros(N, dtype=torch.int32, device=device)
+    for t in range(T):
+        forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **kw)
+        fs[t], mst[t] = forces[0], st
+        res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=Q, R=R, n_traj=N,
+                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"),
+                       p0_kind=None if Pm is None else nv.MAT_DENSE_PER)
+        x, Pm = res.x_final, res.P_final
+        xs[t] = x
+        fst |= res.status
+    return xs, fs, mst, fst

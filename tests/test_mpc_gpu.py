@@ -72,3 +72,28 @@ def test_estimate_state_mpc_solves_for_its_forces_on_the_device():
     kf2.x = x.reshape(12, 1).copy()
     kf2.estimate_state_mpc(imu, p.reshape(12, 1).copy(), dp, ref, contact, f=want)
     assert np.abs(kf.x - kf2.x).max() < 1e-10
+
+
+def test_batched_closed_loop_equals_the_class_loop():
+    """estimate_state_mpc_batch (MPC from the current estimate + one filter step, per step, for all trajectories) against the
+    drop-in class driven trajectory by trajectory."""
+    from optistate_b200.mpc import estimate_state_mpc_batch
+    from optistate_b200.synth import make_streams
+
+    T, N = 6, 3
+    st = make_streams(range(N), T)
+    rng = np.random.default_rng(4)
+    ref = np.zeros((T, 5, 12, N))
+    ref[:, :, 5, :] = 0.28
+    ref[:, :, 0:3, :] = 0.02 * rng.standard_normal((T, 5, 3, N))
+    xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref)
+    torch.cuda.synchronize()
+    assert not (mst & ST_UNPOLISHED).any() and int(fst.max()) == 0
+    for n in range(N):
+        kf = Kalman_Filter()
+        kf.x = kf.x.copy()
+        for t in range(T):
+            x = kf.estimate_state_mpc(st["imu"][t, :, n].reshape(6, 1), st["p"][t, :, n].reshape(12, 1).copy(), st["dp"][t, :, n].reshape(12, 1),
+                                      ref[t, :, :, n].T, st["contact"][t, :, n].reshape(4, 1))
+            assert np.abs(kf.f[:, 0] - fs[t, :, n].cpu().numpy()).max() < 1e-6 * max(1.0, np.abs(kf.f[:, 0]).max()), (n, t)
+            assert np.abs(x.reshape(12) - xs[t, :, n].cpu().numpy()).max() < 1e-7, (n, t)

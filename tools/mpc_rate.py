@@ -1,0 +1,25 @@
+"""Developer helper (GPU box): QPs/s of the batched force MPC.  usage: python tools/mpc_rate.py [n_problems]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from optistate_b200.mpc import mpc_forces  # noqa: E402
+from tests import mpc_cases  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 15
+x, ref, p, c = (torch.from_numpy(a).cuda() for a in mpc_cases.batch(4096, seed=1))
+rep = n // 4096
+x, ref, p, c = x.repeat(1, rep), ref.repeat(1, 1, rep), p.repeat(1, rep), c.repeat(1, rep)
+best = 1e9
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    forces, status = mpc_forces(x, ref, p, c)
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+it = (status >> 8).double()
+print(f"{x.shape[1]} QPs in {best:.2f} ms = {x.shape[1] / best / 1e-3:.3e} QP/s; interior-point iterations mean {it.mean():.1f} max {int(it.max())}; "
+      f"unpolished {int((status & 2).ne(0).sum())}, ipm-limit {int((status & 1).ne(0).sum())}")
