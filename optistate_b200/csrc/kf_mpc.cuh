@@ -32,7 +32,7 @@ constexpr int MPC_MAX_IPM = 40;
 constexpr int MPC_POLISH_ROUNDS = 10;
 constexpr int MPC_MOM_ITERS = 8;
 
-__host__ __device__ constexpr size_t mpc_smem_bytes() { return (size_t)MPC_WARPS * (2 * MPC_TRI + MPC_VEC * MPC_N + 12 * MPC_N) * sizeof(double); }
+__host__ __device__ constexpr size_t mpc_smem_bytes() { return (size_t)MPC_WARPS * (2 * MPC_TRI + MPC_VEC * MPC_N) * sizeof(double); }
 
 __device__ __forceinline__ int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 __device__ __forceinline__ double sym_at(const double *P, int i, int j) { return i >= j ? P[tri_idx(i, j)] : P[tri_idx(j, i)]; }
@@ -76,17 +76,18 @@ __device__ __forceinline__ void rows_gram(const double (&d)[5], double mu, doubl
     gm[5] = d[0] + mu * mu * (d[1] + d[2] + d[3] + d[4]);
 }
 
-// In-place Cholesky of the packed lower triangle (row-major) by one warp; returns false on a non-positive pivot.
-__device__ __forceinline__ bool warp_cholesky(double *M, int lane) {
-    for (int k = 0; k < MPC_N; ++k) {
+// In-place Cholesky of the packed lower triangle (row-major, order n) by one warp; dinv receives 1 / L_kk.  Returns false
+// on a non-positive pivot.
+__device__ __forceinline__ bool warp_cholesky(double *M, double *dinv, int n, int lane) {
+    for (int k = 0; k < n; ++k) {
         const double dkk = M[tri_idx(k, k)];
         if (!(dkk > 0.0)) return false;  // warp-uniform
         const double inv = 1.0 / sqrt(dkk);
         __syncwarp();
-        for (int i = k + 1 + lane; i < MPC_N; i += 32) M[tri_idx(i, k)] *= inv;
-        if (lane == 0) M[tri_idx(k, k)] = dkk * inv;
+        for (int i = k + 1 + lane; i < n; i += 32) M[tri_idx(i, k)] *= inv;
+        if (lane == 0) { M[tri_idx(k, k)] = dkk * inv; dinv[k] = inv; }
         __syncwarp();
-        for (int i = k + 1 + lane; i < MPC_N; i += 32) {
+        for (int i = k + 1 + lane; i < n; i += 32) {
             const double lik = M[tri_idx(i, k)];
             double *row = M + tri_idx(i, 0);
             for (int j = k + 1; j <= i; ++j) row[j] = fma(-lik, M[tri_idx(j, k)], row[j]);
@@ -97,17 +98,17 @@ __device__ __forceinline__ bool warp_cholesky(double *M, int lane) {
 }
 
 // v <- (L L^T)^-1 v, v in shared memory
-__device__ __forceinline__ void warp_chol_solve(const double *L, double *v, int lane) {
-    for (int j = 0; j < MPC_N; ++j) {  // forward, column oriented
+__device__ __forceinline__ void warp_chol_solve(const double *L, const double *dinv, double *v, int n, int lane) {
+    for (int j = 0; j < n; ++j) {  // forward, column oriented
         __syncwarp();
-        const double yj = v[j] / L[tri_idx(j, j)];
+        const double yj = v[j] * dinv[j];
         __syncwarp();
         if (lane == 0) v[j] = yj;
-        for (int i = j + 1 + lane; i < MPC_N; i += 32) v[i] = fma(-L[tri_idx(i, j)], yj, v[i]);
+        for (int i = j + 1 + lane; i < n; i += 32) v[i] = fma(-L[tri_idx(i, j)], yj, v[i]);
     }
-    for (int i = MPC_N - 1; i >= 0; --i) {  // backward: L^T x = y, row i of L updates the entries above it
+    for (int i = n - 1; i >= 0; --i) {  // backward: L^T x = y, row i of L updates the entries above it
         __syncwarp();
-        const double xi = v[i] / L[tri_idx(i, i)];
+        const double xi = v[i] * dinv[i];
         __syncwarp();
         if (lane == 0) v[i] = xi;
         const double *row = L + tri_idx(i, 0);
@@ -116,24 +117,12 @@ __device__ __forceinline__ void warp_chol_solve(const double *L, double *v, int 
     __syncwarp();
 }
 
-// out <- H v for the packed symmetric H (entries of pinned variables are the caller's business)
-__device__ __forceinline__ void warp_symv(const double *H, const double *v, double *out, int lane) {
-    for (int i = lane; i < MPC_N; i += 32) {
+// out <- H v for the packed symmetric H of order n
+__device__ __forceinline__ void warp_symv(const double *H, const double *v, double *out, int n, int lane) {
+    for (int i = lane; i < n; i += 32) {
         double acc = 0.0;
-        for (int j = 0; j < MPC_N; ++j) acc = fma(sym_at(H, i, j), v[j], acc);
+        for (int j = 0; j < n; ++j) acc = fma(sym_at(H, i, j), v[j], acc);
         out[i] = acc;
-    }
-    __syncwarp();
-}
-
-// M <- H with the rows / columns of pinned variables replaced by the identity
-__device__ __forceinline__ void warp_copy_masked(const double *H, double *M, unsigned long long free_mask, int lane) {
-    for (int i = 0; i < MPC_N; ++i) {
-        const bool fi = (free_mask >> i) & 1ull;
-        for (int j = lane; j <= i; j += 32) {
-            const bool fj = (free_mask >> j) & 1ull;
-            M[tri_idx(i, j)] = (fi && fj) ? H[tri_idx(i, j)] : (i == j ? 1.0 : 0.0);
-        }
     }
     __syncwarp();
 }
@@ -143,10 +132,10 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long prob = (long long)blockIdx.x * MPC_WARPS + warp;
     if (prob >= prm.N) return;  // whole warp
-    double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * MPC_TRI + MPC_VEC * MPC_N + 12 * MPC_N);
+    double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * MPC_TRI + MPC_VEC * MPC_N);
     double *H = base, *M = base + MPC_TRI;
     double *u = M + MPC_TRI, *g = u + MPC_N, *rv = g + MPC_N, *dv = rv + MPC_N, *ukeep = dv + MPC_N, *tmp = ukeep + MPC_N;
-    double *Su = tmp + MPC_N;  // [12][MPC_N] sensitivity of the stage state to the forces
+    double *Su = M;  // [12][MPC_N] sensitivity of the stage state to the forces: only needed while H is built, M only after
     const long long N = prm.N;
 
     // ---- problem data --------------------------------------------------------------------------------------
@@ -157,18 +146,35 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         const double c = prm.contact[l * N + prob];
         kind_leg[l] = c == 0.0 ? 0 : (c == 1.0 ? 1 : 2);
     }
-    unsigned long long free_mask = 0ull;
-    for (int v = 0; v < MPC_N; ++v)
-        if (kind_leg[(v % 12) / 3] != 0) free_mask |= 1ull << v;
-    const int my_kind = lane < MPC_NB ? kind_leg[lane % 4] : 0;  // lane b owns block b = 4 * stage + leg
+    // Swing legs carry no force: their unknowns are left out altogether.  Compact unknown 3 (nfl i + r) + c = component c
+    // of the r-th leg that is not in swing at stage i; order n = 15 nfl, nb = 5 nfl blocks, lane b owns block b.
+    int free_leg[4] = {0, 0, 0, 0}, nfl = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        if (kind_leg[l] != 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r == nfl) free_leg[r] = l;
+            ++nfl;
+        }
+    const int n = 15 * nfl, nb = 5 * nfl, ntri = n * (n + 1) / 2;
+    int my_leg = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (nfl > 0 && r == lane % (nfl > 0 ? nfl : 1)) my_leg = free_leg[r];
+    int my_kind = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        if (l == my_leg) my_kind = kind_leg[l];
+    if (lane >= nb) my_kind = 0;
     const bool my_act = my_kind == 1;
     const double mu_f = prm.mu;
 
     // ---- condensed QP: H = 2 sum_i Su_i^T W Su_i + 2 R,  g = 2 sum_i Su_i^T W (sc_i - ref_i) ----------------------
-    for (int e = lane; e < MPC_TRI; e += 32) H[e] = 0.0;
+    for (int e = lane; e < ntri; e += 32) H[e] = 0.0;
     for (int e = lane; e < 12 * MPC_N; e += 32) Su[e] = 0.0;
     __syncwarp();  // the diagonal entries below were zeroed by other lanes
-    for (int e = lane; e < MPC_N; e += 32) { g[e] = 0.0; H[tri_idx(e, e)] = 2.0 * prm.w_force; }
+    for (int e = lane; e < n; e += 32) { g[e] = 0.0; H[tri_idx(e, e)] = 2.0 * prm.w_force; }
     double sc[12];  // free response of the state (replicated in every lane)
 #pragma unroll
     for (int k = 0; k < 12; ++k) sc[k] = prm.x[k * N + prob];
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         double R[9];
         rot_zyx(th[0], th[1], th[2], R);
         // Su <- (I + dt A) Su: rows 0..2 += dt R^T rows 6..8, rows 3..5 += dt rows 9..11 (rows 6..11 unchanged)
-        for (int c = lane; c < MPC_N; c += 32) {
+        for (int c = lane; c < n; c += 32) {
             const double w0 = Su[6 * MPC_N + c], w1 = Su[7 * MPC_N + c], w2 = Su[8 * MPC_N + c];
 #pragma unroll
             for (int a = 0; a < 3; ++a)
@@ -193,8 +199,12 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         }
         __syncwarp();
         // Su[:, 12 i + 3 l + c] += dt B: rows 6..8 = Ihat^-1 skew(R p_l), rows 9..11 = I / m;  Ihat^-1 = R diag(1/I) R^T
-        if (lane < 12) {
-            const int l = lane / 3, c = lane % 3;
+        if (lane < 3 * nfl) {
+            const int c = lane % 3;
+            int l = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r == lane / 3) l = free_leg[r];
             double pw[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) pw[a] = R[3 * a] * pf[3 * l] + R[3 * a + 1] * pf[3 * l + 1] + R[3 * a + 2] * pf[3 * l + 2];
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             double t3[3];  // diag(1/I) R^T sk
 #pragma unroll
             for (int a = 0; a < 3; ++a) t3[a] = prm.inv_inertia[a] * (R[a] * sk[0] + R[3 + a] * sk[1] + R[6 + a] * sk[2]);
-            const int col = 12 * i + lane;
+            const int col = 3 * nfl * i + lane;
 #pragma unroll
             for (int a = 0; a < 3; ++a) Su[(6 + a) * MPC_N + col] += prm.dt * (R[3 * a] * t3[0] + R[3 * a + 1] * t3[1] + R[3 * a + 2] * t3[2]);
             Su[(9 + c) * MPC_N + col] += prm.dt * prm.inv_mass;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < 12; ++k) we[k] = prm.w_state[k] * (sc[k] - prm.body_ref[(i * 12 + k) * N + prob]);
         __syncwarp();
-        const int ncol = 12 * (i + 1);  // later columns of Su are still zero
+        const int ncol = 3 * nfl * (i + 1);  // later columns of Su are still zero
         for (int a = 0; a < ncol; ++a) {
             double sa[12];
 #pragma unroll
@@ -245,23 +255,23 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         __syncwarp();
     }
     double hmax = 0.0, gmax = 0.0;
-    for (int e = lane; e < MPC_N; e += 32) {
+    for (int e = lane; e < n; e += 32) {
         hmax = fmax(hmax, H[tri_idx(e, e)]);
-        if ((free_mask >> e) & 1ull) gmax = fmax(gmax, fabs(g[e]));
+        gmax = fmax(gmax, fabs(g[e]));
     }
     hmax = warp_max(hmax);
     const double gs = fmax(warp_max(gmax), 1e-300);
 
     // ---- interior point ------------------------------------------------------------------------------------------
     const double bvec[5] = {prm.fz_max, 0.0, 0.0, 0.0, 0.0};
-    for (int e = lane; e < MPC_N; e += 32) u[e] = 0.0;
+    for (int e = lane; e < n; e += 32) u[e] = 0.0;
     __syncwarp();
     if (my_act) u[3 * lane + 2] = fmin(10.0, 0.5 * prm.fz_max);  // strictly inside the pyramid
     __syncwarp();
     double s[5], lam[5];
     {
         double au[5];
-        rows_times(u + 3 * (lane < MPC_NB ? lane : 0), mu_f, au);
+        rows_times(u + 3 * (lane < nb ? lane : 0), mu_f, au);
 #pragma unroll
         for (int r = 0; r < 5; ++r) { s[r] = my_act ? bvec[r] - au[r] : 1.0; lam[r] = my_act ? 1.0 / s[r] : 0.0; }
     }
@@ -270,9 +280,9 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     int it = 0;
     for (; it < MPC_MAX_IPM; ++it) {
         // residuals: rd = H u + g + A^T lam (free entries), rp = A u + s - b
-        warp_symv(H, u, rv, lane);
+        warp_symv(H, u, rv, n, lane);
         double rp[5] = {0, 0, 0, 0, 0};
-        if (lane < MPC_NB) {
+        if (lane < nb) {
             double atl[3] = {0, 0, 0};
             if (my_act) {
                 double au[5];
@@ -282,11 +292,11 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 rows_transpose_times(lam, mu_f, atl);
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rv[3 * lane + c] = my_kind != 0 ? rv[3 * lane + c] + g[3 * lane + c] + atl[c] : 0.0;
+            for (int c = 0; c < 3; ++c) rv[3 * lane + c] += g[3 * lane + c] + atl[c];
         }
         __syncwarp();
         double rdmax = 0.0, rpmax = 0.0, comp = 0.0;
-        for (int e = lane; e < MPC_N; e += 32) rdmax = fmax(rdmax, fabs(rv[e]));
+        for (int e = lane; e < n; e += 32) rdmax = fmax(rdmax, fabs(rv[e]));
 #pragma unroll
         for (int r = 0; r < 5; ++r) { rpmax = fmax(rpmax, fabs(rp[r])); comp += my_act ? s[r] * lam[r] : 0.0; }
         rdmax = warp_max(rdmax) / gs;
@@ -294,7 +304,8 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         const double mu_c = m_act > 0.0 ? warp_sum(comp) / m_act : 0.0;
         if (it > 0 && (m_act == 0.0 || mu_c < 1e-9) && fmax(rdmax, rpmax) < 1e-8) break;
         // M = H + A^T (lam / s) A
-        warp_copy_masked(H, M, free_mask, lane);
+        for (int e = lane; e < ntri; e += 32) M[e] = H[e];
+        __syncwarp();
         if (my_act) {
             double d[5], gm[6];
 #pragma unroll
@@ -309,11 +320,11 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             M[tri_idx(o + 2, o + 2)] += gm[5];
         }
         __syncwarp();
-        if (!warp_cholesky(M, lane)) { status |= 1u; break; }
+        if (!warp_cholesky(M, tmp, n, lane)) { status |= 1u; break; }
         if (m_act == 0.0) {  // unconstrained: one Newton step is the answer
-            for (int e = lane; e < MPC_N; e += 32) dv[e] = -rv[e];
-            warp_chol_solve(M, dv, lane);
-            for (int e = lane; e < MPC_N; e += 32) u[e] += dv[e];
+            for (int e = lane; e < n; e += 32) dv[e] = -rv[e];
+            warp_chol_solve(M, tmp, dv, n, lane);
+            for (int e = lane; e < n; e += 32) u[e] += dv[e];
             __syncwarp();
             continue;
         }
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             }
 #pragma unroll
             for (int r = 0; r < 5; ++r) rc[r] = s[r] * lam[r] + (pass == 1 ? ds[r] * dl[r] - sigma_mu : 0.0);
-            for (int e = lane; e < MPC_N; e += 32) dv[e] = -rv[e];
+            for (int e = lane; e < n; e += 32) dv[e] = -rv[e];
             __syncwarp();
             if (my_act) {
                 double t[5], att[3];
@@ -343,7 +354,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 for (int c = 0; c < 3; ++c) dv[3 * lane + c] -= att[c];
             }
             __syncwarp();
-            warp_chol_solve(M, dv, lane);
+            warp_chol_solve(M, tmp, dv, n, lane);
             if (my_act) {
                 double adu[5];
                 rows_times(dv + 3 * lane, mu_f, adu);
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             if (pass == 0) { alpha_aff_p = ap; alpha_aff_d = ad; }
             else {
                 const double a = fmin(fmin(1.0, 0.995 * ap), fmin(1.0, 0.995 * ad));
-                for (int e = lane; e < MPC_N; e += 32) u[e] = fma(a, dv[e], u[e]);
+                for (int e = lane; e < n; e += 32) u[e] = fma(a, dv[e], u[e]);
 #pragma unroll
                 for (int r = 0; r < 5; ++r) { s[r] = fma(a, ds[r], s[r]); lam[r] = fma(a, dl[r], lam[r]); }
             }
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
 
     // ---- polish: method of multipliers on the identified active set, with active-set corrections -------------
     if (m_act > 0.0) {
-        for (int e = lane; e < MPC_N; e += 32) ukeep[e] = u[e];
+        for (int e = lane; e < n; e += 32) ukeep[e] = u[e];
         bool W[5];
         double lw[5];
 #pragma unroll
@@ -383,7 +394,8 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         const double rho = 1e2 * hmax;
         bool ok = false;
         for (int rnd = 0; rnd < MPC_POLISH_ROUNDS && !ok; ++rnd) {
-            warp_copy_masked(H, M, free_mask, lane);
+            for (int e = lane; e < ntri; e += 32) M[e] = H[e];
+            __syncwarp();
             if (my_act) {
                 double d[5], gm[6];
 #pragma unroll
@@ -398,10 +410,10 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 M[tri_idx(o + 2, o + 2)] += gm[5];
             }
             __syncwarp();
-            if (!warp_cholesky(M, lane)) break;
+            if (!warp_cholesky(M, tmp, n, lane)) break;
             double au[5] = {0, 0, 0, 0, 0};
             for (int k = 0; k < MPC_MOM_ITERS; ++k) {
-                for (int e = lane; e < MPC_N; e += 32) dv[e] = ((free_mask >> e) & 1ull) ? -g[e] : 0.0;
+                for (int e = lane; e < n; e += 32) dv[e] = -g[e];
                 __syncwarp();
                 if (my_act) {
                     double t[5], att[3];
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                     for (int c = 0; c < 3; ++c) dv[3 * lane + c] += att[c];
                 }
                 __syncwarp();
-                warp_chol_solve(M, dv, lane);
+                warp_chol_solve(M, tmp, dv, n, lane);
                 if (my_act) {
                     rows_times(dv + 3 * lane, mu_f, au);
 #pragma unroll
@@ -432,14 +444,23 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             ok = !__any_sync(0xffffffffu, change);
         }
         if (ok) {
-            for (int e = lane; e < MPC_N; e += 32) u[e] = dv[e];
+            for (int e = lane; e < n; e += 32) u[e] = dv[e];
         } else {
-            for (int e = lane; e < MPC_N; e += 32) u[e] = ukeep[e];
+            for (int e = lane; e < n; e += 32) u[e] = ukeep[e];
             status |= 2u;
         }
         __syncwarp();
     }
-    for (int e = lane; e < MPC_N; e += 32) prm.forces[(long long)e * N + prob] = ((free_mask >> e) & 1ull) ? u[e] : 0.0;
+    for (int e = lane; e < MPC_N; e += 32) prm.forces[(long long)e * N + prob] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {  // compact -> (stage, leg, component)
+        const int stage = e / (3 * nfl), within = e % (3 * nfl);
+        int l = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r == within / 3) l = free_leg[r];
+        prm.forces[(long long)(12 * stage + 3 * l + within % 3) * N + prob] = u[e];
+    }
     if (prm.status && lane == 0) prm.status[prob] = status | ((uint32_t)it << 8);
 }
 
