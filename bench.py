@@ -381,8 +381,13 @@ def run_native(a):
                                    algo="joint", outputs=("x_final",)))
         n2, T2 = st2["imu"].shape[2], st2["imu"].shape[0]
         del st2
+        from optistate_b200.mpc import mpc_forces
+        from optistate_b200.synth import make_mpc_problems
+
+        qp = [torch.from_numpy(v).to(dev) for v in make_mpc_problems(1 << 15)]
+        tq = once(lambda: mpc_forces(*qp))
         secondary = {"cfg2_1024x10k_f64_steps_per_s": n2 * T2 / t2, "cfg2_seconds": t2,
-                     "joint_path_f64_steps_per_s": (1 << 17) * 200 / tj}
+                     "joint_path_f64_steps_per_s": (1 << 17) * 200 / tj, "force_mpc_qps_per_s": (1 << 15) / tq}
 
     e2e = None
     if not a.no_e2e:

@@ -93,3 +93,23 @@ def monte_carlo_noise(member_ids, q_diag: np.ndarray, r_diag: np.ndarray, nomina
         q[:, j] = q_diag * 10.0 ** rng.uniform(-0.5, 0.5, 12)
         r[:, j] = r_diag * 10.0 ** rng.uniform(-0.5, 0.5, 10)
     return q, r
+
+
+NOMINAL_FEET = np.array([0.2, 0.15, -0.28, 0.2, -0.15, -0.28, -0.2, 0.15, -0.28, -0.2, -0.15, -0.28])
+
+
+def make_mpc_problems(n: int, seed: int = 0):
+    """n force-MPC problems in device layout: x [12, n], body_ref [5, 12, n], p [12, n], contact [4, n].
+    Contact patterns cycle through all 16 combinations; every fourth group of 16 demands a forward velocity that saturates
+    friction and the normal-force cap."""
+    rng = np.random.default_rng(seed)
+    x = np.array([0.02, -0.03, 0.1, 0, 0, 0.27, 0.1, -0.1, 0.05, 0.2, -0.1, 0.0])[:, None] + 0.01 * rng.standard_normal((12, n))
+    ref = np.zeros((5, 12, n))
+    ref[:, 5] = 0.28
+    ref[:, 0:3] = 0.02 * rng.standard_normal((5, 3, n))
+    lateral = np.array([0.0, 0.5, 3.0, -2.0])[(np.arange(n) // 16) % 4]
+    ref[:, 9] = lateral
+    ref[:, 3] = x[3] + lateral * 0.01 * np.arange(1, 6)[:, None]
+    p = NOMINAL_FEET[:, None] + 0.02 * rng.standard_normal((12, n))
+    contact = ((np.arange(n)[None, :] >> np.arange(4)[:, None]) & 1).astype(np.float64)
+    return x, ref, p, contact

@@ -78,3 +78,20 @@ def test_config5_gru_rmse_parity_batched_kf_vs_reference_kf(dtype, tol):
     print("config 5 per-state RMSE (reference-KF arm):", np.array2string(rmse_ref, precision=5))
     print("config 5 |delta RMSE| max:", np.abs(rmse - rmse_ref).max())
     assert np.abs(rmse - rmse_ref).max() < tol * np.abs(rmse_ref).max()
+
+
+def test_example_driver_pipeline_runs_and_is_consistent():
+    """examples/driver_pipeline.py: identification -> filter -> feature rows -> windows, on the device end to end."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "driver_pipeline.py")
+    spec = importlib.util.spec_from_file_location("driver_pipeline", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res, rows, windows = mod.run(n_recordings=8, n_steps=120, seq_len=10)
+    assert res.algo == "sequential" and int(res.status.max()) == 0
+    assert rows.shape == (8, 120, 60) and windows.shape == (8, 111, 10, 60) and windows.dtype == torch.float32
+    assert torch.equal(rows[:, :, 0:12], res.x_steps.permute(2, 0, 1))  # the first 12 feature columns are the estimates
+    w = windows[torch.isfinite(windows)]
+    assert w.min() >= 0.0 and w.max() <= 1.0
