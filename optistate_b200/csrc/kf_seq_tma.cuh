@@ -111,12 +111,12 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
     }
 }
 
-// kSteps: some per-step output (x_steps, x_model_steps, p_world_steps, z_steps, p_trace_steps, k_gain_steps, nis_steps,
-// P_ckpt) is wanted.  Without it those blocks are compiled out instead of being jumped over every step: the taken
-// branches across them cost the lone warp of a scheduler ~10 % of its time in instruction-fetch bubbles (ncu:
-// stall_no_inst / stall_branch_resolving at the branch targets of the 35 KB loop body).
-// kMpc: the covariance model of predict_mpc (element-wise exp transition, cov_predict_mpc_sym) instead of predict's.
-template <typename Real, bool kSummary, bool kSteps, bool kMpc>
+// kOut: which per-step outputs the instantiation can write.  0 = none; 1 = the estimates (x_steps, p_trace_steps,
+// k_gain_steps, nis_steps - what the reference driver records every step); 2 = also the rarely wanted ones
+// (x_model_steps, p_world_steps, z_steps, P_ckpt).  Blocks of outputs that are not wanted are compiled out instead of being
+// jumped over every step: the taken branches across them cost the lone warp of a scheduler ~10 % of its time in
+// instruction-fetch bubbles (ncu: stall_no_inst / stall_branch_resolving at the branch targets of the 35 KB loop body).
+template <typename Real, bool kSummary, int kOut, bool kMpc>
 __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) ? 3 : 2) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         // ---- G0: feet and forces -> mean model --------------------------------------------------------------
         mbar_wait(&bars[0], par);
         propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc,
-                              (kSteps && active) ? prm.p_world_steps : nullptr, (t * 12) * N + i, N);
+                              (kOut == 2 && active) ? prm.p_world_steps : nullptr, (t * 12) * N + i, N);
         Real E[kMpc ? 9 : 1];  // D[a][6 + k] = exp(dt Rb^T[a][k]) - 1 of the predict_mpc transition (kalman_filter.py:153-157)
         if constexpr (kMpc) {
             Real Rb[9];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         }
         __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
         if (more) issue_g0<kMpc>(maps, t + 1, s_warp, g0w, refw, &bars[0], lane);
-        if constexpr (kSteps) {
+        if constexpr (kOut == 2) {
             if (active && prm.x_model_steps) {
 #pragma unroll
                 for (int c = 0; c < NX; ++c) st_traj(prm.x_model_steps, (t * NX + c) * N + i, x[c]);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             if (n_lab) mbar_wait(&bars[2], par);  // G2 (labels, fetched a step ahead like G0 / G1): used inside the last fold
         }
         const Real *z = g1w + lane;
-        if constexpr (kSteps) {
+        if constexpr (kOut == 2) {
             if (active && prm.z_steps) {
 #pragma unroll
                 for (int c = 0; c < NZ; ++c) st_traj(prm.z_steps, (t * NZ + c) * N + i, z[c * 32]);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 #pragma unroll
         for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
 
-        if constexpr (kSteps) {
+        if constexpr (kOut != 0) {
             ptrace = trace_of(P);
             if (prm.k_gain_steps != nullptr) kgain = gain_trace(P, r, nt);
             if (active) {
@@ -342,12 +342,14 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
                 if (prm.p_trace_steps) st_traj(prm.p_trace_steps, t * N + i, ptrace);
                 if (prm.k_gain_steps) st_traj(prm.k_gain_steps, t * N + i, kgain);
                 if (prm.nis_steps) st_traj(prm.nis_steps, t * N + i, nis);
-                if (prm.P_ckpt && prm.ckpt_every > 0 && (t + 1) % prm.ckpt_every == 0) {
-                    const long long base = ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
+                if constexpr (kOut == 2) {
+                    if (prm.P_ckpt && prm.ckpt_every > 0 && (t + 1) % prm.ckpt_every == 0) {
+                        const long long base = ((t + 1) / prm.ckpt_every - 1) * (long long)(NX * NX) * N + i;
 #pragma unroll
-                    for (int a = 0; a < NX; ++a)
+                        for (int a = 0; a < NX; ++a)
 #pragma unroll
-                        for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
+                            for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
+                    }
                 }
             }
         }
