@@ -76,22 +76,31 @@ __device__ __forceinline__ void rows_gram(const double (&d)[5], double mu, doubl
     gm[5] = d[0] + mu * mu * (d[1] + d[2] + d[3] + d[4]);
 }
 
-// In-place Cholesky of the packed lower triangle (row-major, order n) by one warp; dinv receives 1 / L_kk.  Returns false
-// on a non-positive pivot.
+// In-place Cholesky of the packed lower triangle (row-major, order n) by one warp, left-looking: column k is produced
+// from the finished columns to its left, lane by row, as a dot product of two rows - two shared-memory loads per FMA and
+// one store per ENTRY (the right-looking form re-writes the whole trailing matrix at every step: a store per FMA).  dinv
+// receives 1 / L_kk.  Returns false on a non-positive pivot.
 __device__ __forceinline__ bool warp_cholesky(double *M, double *dinv, int n, int lane) {
     for (int k = 0; k < n; ++k) {
-        const double dkk = M[tri_idx(k, k)];
+        const double *rk = M + tri_idx(k, 0);
+        for (int i = k + lane; i < n; i += 32) {
+            double *ri = M + tri_idx(i, 0);
+            double a0 = ri[k], a1 = 0.0;
+            int j = 0;
+            for (; j + 1 < k; j += 2) {
+                a0 = fma(-ri[j], rk[j], a0);
+                a1 = fma(-ri[j + 1], rk[j + 1], a1);
+            }
+            if (j < k) a0 = fma(-ri[j], rk[j], a0);
+            ri[k] = a0 + a1;
+        }
+        __syncwarp();
+        const double dkk = rk[k];
         if (!(dkk > 0.0)) return false;  // warp-uniform
         const double inv = 1.0 / sqrt(dkk);
         __syncwarp();
         for (int i = k + 1 + lane; i < n; i += 32) M[tri_idx(i, k)] *= inv;
         if (lane == 0) { M[tri_idx(k, k)] = dkk * inv; dinv[k] = inv; }
-        __syncwarp();
-        for (int i = k + 1 + lane; i < n; i += 32) {
-            const double lik = M[tri_idx(i, k)];
-            double *row = M + tri_idx(i, 0);
-            for (int j = k + 1; j <= i; ++j) row[j] = fma(-lik, M[tri_idx(j, k)], row[j]);
-        }
         __syncwarp();
     }
     return true;
