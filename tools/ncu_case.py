@@ -1,5 +1,5 @@
 """Developer helper (GPU box): run a few single kf_batch launches so that ncu can capture them.
-usage: python tools/ncu_case.py f64:tma:x_final f32:direct:summary ...   (env CASE_N, CASE_T, CASE_S)"""
+usage: python tools/ncu_case.py f64:tma:x_final f32:direct:summary f64:tma-mpc:x_steps ...   (env CASE_N, CASE_T, CASE_S)"""
 import os
 import sys
 
@@ -17,6 +17,9 @@ for spec in sys.argv[1:]:
     dt = torch.float64 if dt_name == "f64" else torch.float32
     dev = {k: torch.from_numpy(v).to("cuda", dt) for k, v in st.items()}
     kw = {}
+    if mode.endswith("-mpc"):  # predict_mpc covariance model
+        mode = mode[:-4]
+        kw.update(cov_model="mpc", body_ref=dev["truth"])
     if mode == "joint":
         kw["algo"] = "joint"
     if mode == "direct":
