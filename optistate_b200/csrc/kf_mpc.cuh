@@ -9,11 +9,11 @@
 //
 // The reference hands this to CasADi + qpOASES (an active-set solver), neither of which exists offline: PARITY UNPINNED.  The
 // QP is strictly convex (R > 0), so its minimiser is unique and any exact solver agrees with qpOASES to solver tolerance.
-// Here: the condensed Hessian H (packed lower triangle, 1,830 doubles) and gradient g are built in shared memory, a
-// Mehrotra predictor-corrector interior-point method brings the iterate to complementarity ~1e-9, and a polish phase
-// (method of multipliers on the identified active set, with active-set corrections) removes the interior-point bias:
-// <= 2e-10 of max|u| against an independent active-set solve (oracle/mpc_numpy.py) on 400 random problems in the NumPy
-// prototype of exactly this procedure.  The normal-equations matrix H + A^T D A only ever gains 3x3 diagonal blocks, because
+// Here: swing legs are left out of the unknowns (order n = 15 x legs not in swing), the condensed Hessian H (packed lower
+// triangle, <= 1,830 doubles) and gradient g are built in shared memory, a Mehrotra predictor-corrector interior-point
+// method brings the iterate to complementarity ~1e-9, and a polish phase (method of multipliers on the identified active
+// set, with active-set corrections) removes the interior-point bias: <= 3e-10 of max|u| against an independent active-set
+// solve (oracle/mpc_numpy.py) over 256 problems covering every contact pattern (tests/test_mpc_gpu.py).  The normal-equations matrix H + A^T D A only ever gains 3x3 diagonal blocks, because
 // every constraint row touches one leg of one stage.
 #pragma once
 
@@ -24,10 +24,9 @@ namespace okf {
 
 constexpr int MPC_NH = 5;
 constexpr int MPC_N = 12 * MPC_NH;                  // unknowns
-constexpr int MPC_NB = 4 * MPC_NH;                  // (stage, leg) blocks of three unknowns
 constexpr int MPC_TRI = MPC_N * (MPC_N + 1) / 2;    // packed lower triangle
 constexpr int MPC_WARPS = 2;                        // problems per block
-constexpr int MPC_VEC = 6;                          // per-warp vectors of MPC_N doubles: u, g, r, d, u_keep, tmp
+constexpr int MPC_VEC = 6;                          // per-warp vectors of MPC_N doubles: u, g, r, d, u_keep, 1 / pivots
 constexpr int MPC_MAX_IPM = 40;
 constexpr int MPC_POLISH_ROUNDS = 10;
 constexpr int MPC_MOM_ITERS = 8;
@@ -143,7 +142,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     if (prob >= prm.N) return;  // whole warp
     double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * MPC_TRI + MPC_VEC * MPC_N);
     double *H = base, *M = base + MPC_TRI;
-    double *u = M + MPC_TRI, *g = u + MPC_N, *rv = g + MPC_N, *dv = rv + MPC_N, *ukeep = dv + MPC_N, *tmp = ukeep + MPC_N;
+    double *u = M + MPC_TRI, *g = u + MPC_N, *rv = g + MPC_N, *dv = rv + MPC_N, *ukeep = dv + MPC_N, *dinv = ukeep + MPC_N;
     double *Su = M;  // [12][MPC_N] sensitivity of the stage state to the forces: only needed while H is built, M only after
     const long long N = prm.N;
 
@@ -329,10 +328,10 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             M[tri_idx(o + 2, o + 2)] += gm[5];
         }
         __syncwarp();
-        if (!warp_cholesky(M, tmp, n, lane)) { status |= 1u; break; }
+        if (!warp_cholesky(M, dinv, n, lane)) { status |= 1u; break; }
         if (m_act == 0.0) {  // unconstrained: one Newton step is the answer
             for (int e = lane; e < n; e += 32) dv[e] = -rv[e];
-            warp_chol_solve(M, tmp, dv, n, lane);
+            warp_chol_solve(M, dinv, dv, n, lane);
             for (int e = lane; e < n; e += 32) u[e] += dv[e];
             __syncwarp();
             continue;
@@ -363,7 +362,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 for (int c = 0; c < 3; ++c) dv[3 * lane + c] -= att[c];
             }
             __syncwarp();
-            warp_chol_solve(M, tmp, dv, n, lane);
+            warp_chol_solve(M, dinv, dv, n, lane);
             if (my_act) {
                 double adu[5];
                 rows_times(dv + 3 * lane, mu_f, adu);
@@ -419,7 +418,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 M[tri_idx(o + 2, o + 2)] += gm[5];
             }
             __syncwarp();
-            if (!warp_cholesky(M, tmp, n, lane)) break;
+            if (!warp_cholesky(M, dinv, n, lane)) break;
             double au[5] = {0, 0, 0, 0, 0};
             for (int k = 0; k < MPC_MOM_ITERS; ++k) {
                 for (int e = lane; e < n; e += 32) dv[e] = -g[e];
@@ -433,7 +432,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                     for (int c = 0; c < 3; ++c) dv[3 * lane + c] += att[c];
                 }
                 __syncwarp();
-                warp_chol_solve(M, tmp, dv, n, lane);
+                warp_chol_solve(M, dinv, dv, n, lane);
                 if (my_act) {
                     rows_times(dv + 3 * lane, mu_f, au);
 #pragma unroll
