@@ -226,11 +226,14 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *desc, void *cuda_strea
  * active-set solve).  FP64 only. ---- */
 #define OPTI_KF_MPC_HORIZON 5
 enum { OPTI_KF_MPC_ST_IPM_LIMIT = 1,  /* interior-point phase stopped on its iteration cap or a pivot breakdown       */
-       OPTI_KF_MPC_ST_UNPOLISHED = 2  /* active-set polish did not settle: the forces are the interior-point iterate
-                                         (~1e-6 relative) instead of the exact vertex solution                         */ };
+       OPTI_KF_MPC_ST_UNPOLISHED = 2, /* active-set polish did not settle: the forces are the interior-point iterate
+                                         (~1e-6 relative) instead of the exact vertex solution                         */
+       OPTI_KF_MPC_ST_TOO_MANY_LEGS = 4 /* more legs out of swing than max_free_legs promised: forces are NaN          */ };
 typedef struct OptiKfMpcDesc {
     uint32_t struct_size, abi_version;
-    int32_t dtype, reserved;       /* OPTI_KF_F64 */
+    int32_t dtype;                 /* OPTI_KF_F64 */
+    int32_t max_free_legs;         /* bound on the legs with contact != 0 in any problem (1..4; 0 = unknown = 4): sizes the
+                                      kernel's shared memory, i.e. its occupancy - a trot needs 2                       */
     int64_t n_problems;
     const void *x;                 /* [12][N] current state (column 0 of body_mpc, kalman_filter.py:143)              */
     const void *body_ref;          /* [5][12][N] reference states of the horizon (columns 1..5 of body_mpc)           */

@@ -464,7 +464,7 @@ int optistate_kf_mpc_forces(const OptiKfMpcDesc *d, void *cuda_stream) {
     if (!d) return OPTI_KF_E_NULL;
     if (d->struct_size != sizeof(OptiKfMpcDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
     if (d->dtype != OPTI_KF_F64) return OPTI_KF_E_DTYPE;  // cond(H) ~ 1e5: the QP is solved in double only
-    if (d->n_problems < 0) return OPTI_KF_E_SHAPE;
+    if (d->n_problems < 0 || d->max_free_legs < 0 || d->max_free_legs > 4) return OPTI_KF_E_SHAPE;
     if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0) || !(d->mu > 0) ||
         !(d->fz_max > 0) || !(d->w_force > 0))
         return OPTI_KF_E_SHAPE;
@@ -475,6 +475,7 @@ int optistate_kf_mpc_forces(const OptiKfMpcDesc *d, void *cuda_stream) {
     okf::MpcParams p;
     std::memset(&p, 0, sizeof p);
     p.N = d->n_problems;
+    p.max_legs = d->max_free_legs == 0 ? 4 : d->max_free_legs;
     p.x = (const double *)d->x; p.body_ref = (const double *)d->body_ref; p.p = (const double *)d->p;
     p.contact = (const double *)d->contact; p.forces = (double *)d->forces; p.status = d->status;
     p.dt = d->dt; p.inv_mass = 1.0 / d->mass; p.gravity = d->gravity; p.mu = d->mu; p.fz_max = d->fz_max; p.w_force = d->w_force;

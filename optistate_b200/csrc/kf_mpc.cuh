@@ -28,10 +28,17 @@ constexpr int MPC_TRI = MPC_N * (MPC_N + 1) / 2;    // packed lower triangle
 constexpr int MPC_WARPS = 2;                        // problems per block
 constexpr int MPC_VEC = 6;                          // per-warp vectors of MPC_N doubles: u, g, r, d, u_keep, 1 / pivots
 constexpr int MPC_MAX_IPM = 40;
-constexpr int MPC_POLISH_ROUNDS = 10;
+constexpr int MPC_POLISH_ROUNDS = 16;
 constexpr int MPC_MOM_ITERS = 8;
 
-__host__ __device__ constexpr size_t mpc_smem_bytes() { return (size_t)MPC_WARPS * (2 * MPC_TRI + MPC_VEC * MPC_N) * sizeof(double); }
+// Shared memory is sized for the largest number of legs not in swing that the batch contains (max_legs, 1..4; the host
+// passes 4 when it does not know): order nmax = 15 max_legs.  A trot (two stance legs) then needs 9 KB per problem
+// instead of 32 KB, which is what decides how many warps an SM can hold for this latency-bound kernel.
+__host__ __device__ constexpr int mpc_mat_doubles(int max_legs) {  // H or M: packed triangle; M also hosts the 12 x nmax sensitivities
+    return (15 * max_legs) * (15 * max_legs + 1) / 2 > 12 * 15 * max_legs ? (15 * max_legs) * (15 * max_legs + 1) / 2 : 12 * 15 * max_legs;
+}
+__host__ __device__ constexpr int mpc_warp_doubles(int max_legs) { return 2 * mpc_mat_doubles(max_legs) + MPC_VEC * 15 * max_legs; }
+__host__ __device__ constexpr size_t mpc_smem_bytes(int max_legs) { return (size_t)MPC_WARPS * mpc_warp_doubles(max_legs) * sizeof(double); }
 
 __device__ __forceinline__ int tri_idx(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 __device__ __forceinline__ double sym_at(const double *P, int i, int j) { return i >= j ? P[tri_idx(i, j)] : P[tri_idx(j, i)]; }
@@ -140,10 +147,11 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long prob = (long long)blockIdx.x * MPC_WARPS + warp;
     if (prob >= prm.N) return;  // whole warp
-    double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * MPC_TRI + MPC_VEC * MPC_N);
-    double *H = base, *M = base + MPC_TRI;
-    double *u = M + MPC_TRI, *g = u + MPC_N, *rv = g + MPC_N, *dv = rv + MPC_N, *ukeep = dv + MPC_N, *dinv = ukeep + MPC_N;
-    double *Su = M;  // [12][MPC_N] sensitivity of the stage state to the forces: only needed while H is built, M only after
+    const int nmax = 15 * prm.max_legs, ld = nmax;  // ld: row stride of the sensitivities
+    double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * mpc_warp_doubles(prm.max_legs);
+    double *H = base, *M = base + mpc_mat_doubles(prm.max_legs);
+    double *u = M + mpc_mat_doubles(prm.max_legs), *g = u + nmax, *rv = g + nmax, *dv = rv + nmax, *ukeep = dv + nmax, *dinv = ukeep + nmax;
+    double *Su = M;  // [12][nmax] sensitivity of the stage state to the forces: only needed while H is built, M only after
     const long long N = prm.N;
 
     // ---- problem data --------------------------------------------------------------------------------------
@@ -165,6 +173,11 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 if (r == nfl) free_leg[r] = l;
             ++nfl;
         }
+    if (nfl > prm.max_legs) {  // the caller's bound on the legs not in swing is wrong for this problem: no answer
+        for (int e = lane; e < MPC_N; e += 32) prm.forces[(long long)e * N + prob] = __longlong_as_double(0x7ff8000000000000LL);
+        if (prm.status && lane == 0) prm.status[prob] = 4u;
+        return;
+    }
     const int n = 15 * nfl, nb = 5 * nfl, ntri = n * (n + 1) / 2;
     int my_leg = 0;
 #pragma unroll
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
 
     // ---- condensed QP: H = 2 sum_i Su_i^T W Su_i + 2 R,  g = 2 sum_i Su_i^T W (sc_i - ref_i) ----------------------
     for (int e = lane; e < ntri; e += 32) H[e] = 0.0;
-    for (int e = lane; e < 12 * MPC_N; e += 32) Su[e] = 0.0;
+    for (int e = lane; e < 12 * ld; e += 32) Su[e] = 0.0;
     __syncwarp();  // the diagonal entries below were zeroed by other lanes
     for (int e = lane; e < n; e += 32) { g[e] = 0.0; H[tri_idx(e, e)] = 2.0 * prm.w_force; }
     double sc[12];  // free response of the state (replicated in every lane)
@@ -198,12 +211,12 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         rot_zyx(th[0], th[1], th[2], R);
         // Su <- (I + dt A) Su: rows 0..2 += dt R^T rows 6..8, rows 3..5 += dt rows 9..11 (rows 6..11 unchanged)
         for (int c = lane; c < n; c += 32) {
-            const double w0 = Su[6 * MPC_N + c], w1 = Su[7 * MPC_N + c], w2 = Su[8 * MPC_N + c];
+            const double w0 = Su[6 * ld + c], w1 = Su[7 * ld + c], w2 = Su[8 * ld + c];
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-                Su[a * MPC_N + c] += prm.dt * (R[0 * 3 + a] * w0 + R[1 * 3 + a] * w1 + R[2 * 3 + a] * w2);  // R^T[a][k] = R[k][a]
+                Su[a * ld + c] += prm.dt * (R[0 * 3 + a] * w0 + R[1 * 3 + a] * w1 + R[2 * 3 + a] * w2);  // R^T[a][k] = R[k][a]
 #pragma unroll
-            for (int a = 0; a < 3; ++a) Su[(3 + a) * MPC_N + c] += prm.dt * Su[(9 + a) * MPC_N + c];
+            for (int a = 0; a < 3; ++a) Su[(3 + a) * ld + c] += prm.dt * Su[(9 + a) * ld + c];
         }
         __syncwarp();
         // Su[:, 12 i + 3 l + c] += dt B: rows 6..8 = Ihat^-1 skew(R p_l), rows 9..11 = I / m;  Ihat^-1 = R diag(1/I) R^T
@@ -226,8 +239,8 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
             for (int a = 0; a < 3; ++a) t3[a] = prm.inv_inertia[a] * (R[a] * sk[0] + R[3 + a] * sk[1] + R[6 + a] * sk[2]);
             const int col = 3 * nfl * i + lane;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) Su[(6 + a) * MPC_N + col] += prm.dt * (R[3 * a] * t3[0] + R[3 * a + 1] * t3[1] + R[3 * a + 2] * t3[2]);
-            Su[(9 + c) * MPC_N + col] += prm.dt * prm.inv_mass;
+            for (int a = 0; a < 3; ++a) Su[(6 + a) * ld + col] += prm.dt * (R[3 * a] * t3[0] + R[3 * a + 1] * t3[1] + R[3 * a + 2] * t3[2]);
+            Su[(9 + c) * ld + col] += prm.dt * prm.inv_mass;
         }
         // free response: sc <- (I + dt A) sc + dt g
         {
@@ -246,18 +259,18 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
         for (int a = 0; a < ncol; ++a) {
             double sa[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) sa[k] = prm.w_state[k] * Su[k * MPC_N + a];
+            for (int k = 0; k < 12; ++k) sa[k] = prm.w_state[k] * Su[k * ld + a];
             for (int b = lane; b <= a; b += 32) {
                 double acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < 12; ++k) acc = fma(sa[k], Su[k * MPC_N + b], acc);
+                for (int k = 0; k < 12; ++k) acc = fma(sa[k], Su[k * ld + b], acc);
                 H[tri_idx(a, b)] += 2.0 * acc;
             }
         }
         for (int a = lane; a < ncol; a += 32) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 12; ++k) acc = fma(Su[k * MPC_N + a], we[k], acc);
+            for (int k = 0; k < 12; ++k) acc = fma(Su[k * ld + a], we[k], acc);
             g[a] += 2.0 * acc;
         }
         __syncwarp();
@@ -440,16 +453,41 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
                 }
                 __syncwarp();
             }
-            bool change = false;
+            // active-set correction.  The first two rounds take every violated constraint in and every negative multiplier
+            // out at once (one round is almost always enough); after that ONE change per round - the most violated
+            // constraint, or else the most negative multiplier - because simultaneous changes can cycle.
+            bool infeas[5], neg[5], any_inf = false, any_neg = false;
+            double worst_inf = 0.0, worst_neg = 0.0;
+            int r_inf = -1, r_neg = -1;
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
-                const bool infeas = my_act && !W[r] && au[r] - bvec[r] > 1e-9 * prm.fz_max;
-                const bool neg = W[r] && lw[r] < -1e-9 * gs;
-                if (infeas) { W[r] = true; lw[r] = 0.0; }
-                if (neg) { W[r] = false; lw[r] = 0.0; }
-                change |= infeas || neg;
+                infeas[r] = my_act && !W[r] && au[r] - bvec[r] > 1e-9 * prm.fz_max;
+                neg[r] = W[r] && lw[r] < -1e-9 * gs;
+                any_inf |= infeas[r];
+                any_neg |= neg[r];
+                if (infeas[r] && au[r] - bvec[r] > worst_inf) { worst_inf = au[r] - bvec[r]; r_inf = r; }
+                if (neg[r] && lw[r] < worst_neg) { worst_neg = lw[r]; r_neg = r; }
             }
-            ok = !__any_sync(0xffffffffu, change);
+            const bool warp_inf = __any_sync(0xffffffffu, any_inf), warp_neg = __any_sync(0xffffffffu, any_neg);
+            ok = !warp_inf && !warp_neg;
+            if (!ok && rnd < 2) {
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    if (infeas[r]) { W[r] = true; lw[r] = 0.0; }
+                    if (neg[r]) { W[r] = false; lw[r] = 0.0; }
+                }
+            } else if (!ok) {
+                const double mine = warp_inf ? worst_inf : -worst_neg;           // >= 0, larger is worse
+                const double worst = warp_max(mine);
+                const unsigned cand = __ballot_sync(0xffffffffu, (warp_inf ? r_inf : r_neg) >= 0 && mine == worst);
+                if (lane == __ffs(cand) - 1) {
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        if (warp_inf && r == r_inf) { W[r] = true; lw[r] = 0.0; }
+                        if (!warp_inf && r == r_neg) { W[r] = false; lw[r] = 0.0; }
+                    }
+                }
+            }
         }
         if (ok) {
             for (int e = lane; e < n; e += 32) u[e] = dv[e];

@@ -7,6 +7,7 @@ namespace okf {
 
 struct MpcParams {
     long long N;
+    int max_legs;                               // 1..4: bound on the legs not in swing of any problem (sizes shared memory)
     const double *x, *body_ref, *p, *contact;  // [12][N], [NH*12][N], [12][N], [4][N]
     double *forces;                             // [NH*12][N]
     uint32_t *status;                           // [N] optional

@@ -326,13 +326,14 @@ int kf_identify_noise(int64_t dtype, int64_t n_traj, int64_t n_steps, int64_t n_
 }
 
 // Convex force MPC: x [12][N], body_ref [5][12][N], p [12][N], contact [4][N] -> forces [5][12][N], status [N]
-int kf_mpc_forces(int64_t n, const std::map<std::string, double> &consts, const std::vector<double> &w_state, const TensorMap &tensors) {
+int kf_mpc_forces(int64_t n, int64_t max_free_legs, const std::map<std::string, double> &consts, const std::vector<double> &w_state, const TensorMap &tensors) {
     OptiKfMpcDesc d;
     std::memset(&d, 0, sizeof d);
     d.struct_size = sizeof d;
     d.abi_version = OPTISTATE_KF_ABI_VERSION;
     d.dtype = OPTI_KF_F64;
     d.n_problems = n;
+    d.max_free_legs = (int32_t)max_free_legs;
     auto x = tensors.find("x");
     TORCH_CHECK(x != tensors.end() && x->second.is_cuda(), "optistate_b200: 'x' must be a CUDA tensor (there is no CPU path)");
     TORCH_CHECK(w_state.size() == 12, "optistate_b200: w_state needs 12 entries");

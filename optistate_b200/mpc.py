@@ -18,7 +18,7 @@ W_STATE = (10.0, 10.0, 10.0, 100.0, 100.0, 100.0, 1.0, 1.0, 5.0, 1.0, 1.0, 1.0)
 W_FORCE = 1e-6
 MU = 0.6
 FZ_MAX = 150.0
-ST_IPM_LIMIT, ST_UNPOLISHED = 1, 2
+ST_IPM_LIMIT, ST_UNPOLISHED, ST_TOO_MANY_LEGS = 1, 2, 4
 
 
 def _dev64(a, device):
@@ -28,11 +28,12 @@ def _dev64(a, device):
 
 def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
                gravity: float = INITIAL_PARAMS.GRAVITY, mu: float = MU, fz_max: float = FZ_MAX, w_state=W_STATE, w_force: float = W_FORCE,
-               device=None):
+               max_free_legs=None, device=None):
     """Solves N force MPC problems.
 
     x [12, N] current states; body_ref [5, 12, N] reference states of the horizon; p [12, N] body-frame feet;
-    contact [4, N] (0 swing, 1 stance).  Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]:
+    contact [4, N] (0 swing, 1 stance).  max_free_legs: bound on the legs out of swing in any problem (None = taken from
+    `contact`, which costs one small reduction and a host sync; it sizes the kernel's shared memory).  Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]:
     ST_* bits | interior-point iterations << 8).
     """
     nv.require_cuda()
@@ -40,13 +41,15 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
     x_t, p_t, c_t, b_t = _dev64(x, device), _dev64(p, device), _dev64(contact, device), _dev64(body_ref, device)
     n = x_t.shape[-1] if x_t.dim() == 2 else 1
     x_t, p_t, c_t, b_t = x_t.reshape(12, n), p_t.reshape(12, n), c_t.reshape(4, n), b_t.reshape(HORIZON, 12, n)
+    if max_free_legs is None:
+        max_free_legs = max(1, int((c_t != 0).sum(dim=0).max())) if n > 0 else 4
     forces = torch.empty((HORIZON, 12, n), dtype=torch.float64, device=device)
     status = torch.zeros(n, dtype=torch.int32, device=device)
     inertia = np.diag(INITIAL_PARAMS.INERTIA_ROT) if inertia is None else np.asarray(inertia, float).reshape(3)
     consts = dict(dt=float(dt), mass=float(mass), inertia0=float(inertia[0]), inertia1=float(inertia[1]), inertia2=float(inertia[2]),
                   gravity=float(gravity), mu=float(mu), fz_max=float(fz_max), w_force=float(w_force))
     with torch.cuda.device(device):
-        nv.check(int(nv.ext().kf_mpc_forces(n, consts, [float(w) for w in w_state],
+        nv.check(int(nv.ext().kf_mpc_forces(n, int(max_free_legs), consts, [float(w) for w in w_state],
                                             dict(x=x_t, body_ref=b_t, p=p_t, contact=c_t, forces=forces, status=status))),
                  "optistate_kf_mpc_forces")
     return forces, status

@@ -45,7 +45,7 @@ def test_mpc_descriptor_validation():
     P, D = ctypes.c_void_p, ctypes.c_double
 
     class Desc(ctypes.Structure):
-        _fields_ = [("struct_size", ctypes.c_uint32), ("abi_version", ctypes.c_uint32), ("dtype", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        _fields_ = [("struct_size", ctypes.c_uint32), ("abi_version", ctypes.c_uint32), ("dtype", ctypes.c_int32), ("max_free_legs", ctypes.c_int32),
                     ("n_problems", ctypes.c_int64), ("x", P), ("body_ref", P), ("p", P), ("contact", P), ("forces", P), ("status", P),
                     ("dt", D), ("mass", D), ("inertia", D * 3), ("gravity", D), ("mu", D), ("fz_max", D), ("w_state", D * 12), ("w_force", D)]
 
@@ -58,6 +58,9 @@ def test_mpc_descriptor_validation():
     assert lib.optistate_kf_mpc_forces(ctypes.byref(d), None) == -3  # FP64 only
     d.dtype, d.mu = 0, 0.0
     assert lib.optistate_kf_mpc_forces(ctypes.byref(d), None) == -4
+    d.mu, d.max_free_legs = 0.6, 5
+    assert lib.optistate_kf_mpc_forces(ctypes.byref(d), None) == -4
+    d.max_free_legs = 2
     d.mu, d.n_problems = 0.6, 0
     assert lib.optistate_kf_mpc_forces(ctypes.byref(d), None) == 0   # nothing to do
     d.struct_size -= 8

@@ -97,3 +97,37 @@ def test_batched_closed_loop_equals_the_class_loop():
                                       ref[t, :, :, n].T, st["contact"][t, :, n].reshape(4, 1))
             assert np.abs(kf.f[:, 0] - fs[t, :, n].cpu().numpy()).max() < 1e-6 * max(1.0, np.abs(kf.f[:, 0]).max()), (n, t)
             assert np.abs(x.reshape(12) - xs[t, :, n].cpu().numpy()).max() < 1e-7, (n, t)
+
+
+def test_shared_memory_bound_on_the_legs_out_of_swing():
+    """max_free_legs sizes the kernel's shared memory: same forces with the tight bound, a flagged NaN when it is wrong."""
+    from optistate_b200.mpc import ST_TOO_MANY_LEGS
+
+    x, ref, p, c = mpc_cases.batch(64, seed=7)
+    c[:] = np.array([1.0, 0.0, 0.0, 1.0])[:, None]  # a trot: two legs in stance
+    loose, _ = mpc_forces(x, ref, p, c, max_free_legs=4)
+    tight, st = mpc_forces(x, ref, p, c)              # bound taken from the contact array: 2
+    assert torch.equal(loose, tight) and not (st & 7).any()
+    c[:, 5] = 1.0                                      # one problem with four legs in stance, but the caller promises two
+    wrong, st = mpc_forces(x, ref, p, c, max_free_legs=2)
+    assert int(st[5]) == ST_TOO_MANY_LEGS and torch.isnan(wrong[:, :, 5]).all()
+    keep = torch.arange(64) != 5
+    assert torch.equal(wrong[:, :, keep], tight[:, :, keep])
+
+
+def test_trot_batch_polishes_every_problem():
+    """4,096 trot problems; number 833 made simultaneous active-set corrections cycle (period 4) until the corrections were
+    limited to one change per round after the second round."""
+    x, ref, p, c = mpc_cases.batch(4096, seed=1)
+    c[:] = np.where((np.arange(4096) % 2 == 0)[None, :], np.array([1.0, 0, 0, 1])[:, None], np.array([0, 1.0, 1, 0])[:, None])
+    forces, status = mpc_forces(x, ref, p, c)
+    F, st = forces.cpu().numpy(), status.cpu().numpy()
+    assert not (st & 7).any(), np.where(st & 7)[0]
+    for k in [833] + list(range(0, 4096, 128)):
+        H, g, _ = mpc.build_qp(x[:, k], ref[:, :, k].T, p[:, k])
+        A, b, pinned = mpc.constraints(c[:, k])
+        want = mpc.solve_ldp(H, g, A, b, pinned)
+        u = F[:, :, k].reshape(-1)
+        assert np.abs(u - want).max() < 1e-8 * max(1.0, np.abs(want).max()), k
+        viol, stat = mpc.kkt_certificate(u, H, g, A, b, pinned)
+        assert viol < 1e-7 and stat < 1e-8, (k, viol, stat)

@@ -1,4 +1,4 @@
-"""Developer helper (GPU box): QPs/s of the batched force MPC.  usage: python tools/mpc_rate.py [n_problems]"""
+"""Developer helper (GPU box): QPs/s of the batched force MPC.  usage: python tools/mpc_rate.py [n_problems] [trot]"""
 import os
 import sys
 
@@ -12,6 +12,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 15
 x, ref, p, c = (torch.from_numpy(a).cuda() for a in mpc_cases.batch(4096, seed=1))
 rep = n // 4096
 x, ref, p, c = x.repeat(1, rep), ref.repeat(1, 1, rep), p.repeat(1, rep), c.repeat(1, rep)
+if len(sys.argv) > 2 and sys.argv[2] == "trot":  # the gait of the recordings: diagonal leg pairs alternate
+    c = torch.where((torch.arange(c.shape[1], device=c.device) % 2 == 0)[None, :], torch.tensor([1.0, 0, 0, 1], device=c.device, dtype=c.dtype)[:, None],
+                    torch.tensor([0, 1.0, 1, 0], device=c.device, dtype=c.dtype)[:, None]).contiguous()
 best = 1e9
 for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
