@@ -386,8 +386,12 @@ def run_native(a):
 
         qp = [torch.from_numpy(v).to(dev) for v in make_mpc_problems(1 << 15)]
         tq = once(lambda: mpc_forces(*qp))
+        trot = torch.where((torch.arange(1 << 15, device=dev) % 2 == 0)[None, :], torch.tensor([1.0, 0, 0, 1], device=dev, dtype=torch.float64)[:, None],
+                           torch.tensor([0, 1.0, 1, 0], device=dev, dtype=torch.float64)[:, None]).contiguous()
+        tqt = once(lambda: mpc_forces(qp[0], qp[1], qp[2], trot))
         secondary = {"cfg2_1024x10k_f64_steps_per_s": n2 * T2 / t2, "cfg2_seconds": t2,
-                     "joint_path_f64_steps_per_s": (1 << 17) * 200 / tj, "force_mpc_qps_per_s": (1 << 15) / tq}
+                     "joint_path_f64_steps_per_s": (1 << 17) * 200 / tj, "force_mpc_qps_per_s": (1 << 15) / tq,
+                     "force_mpc_trot_qps_per_s": (1 << 15) / tqt}
 
     e2e = None
     if not a.no_e2e:
