@@ -422,3 +422,29 @@ def test_custom_model_constants_and_degenerate_sizes(algo):
     assert np.allclose(empty_t.x_final.cpu().numpy(), cases.START[:, None]) and np.allclose(empty_t.P_matrix()[0].cpu().numpy(), cases.Q_DEFAULT)
     empty_n = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], n_traj=0, algo=algo, outputs=("x_final",))
     assert empty_n.x_final.shape == (12, 0)
+
+
+def test_bench_native_arm_prints_the_contract_line():
+    """bench.py on a small workload: every key of the measurement contract is present and self-consistent."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--traj-per-gpu", "8192", "--T", "60",
+                          "--streams", "128", "--no-cpu-baseline"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["metric"] == "kf_trajectory_steps_per_sec" and d["unit"] == "trajectory-steps/s" and d["n_gpus"] == 1 and d["dtype"] == "f64"
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
+    assert abs(d["value"] - 8192 * 60 * 2 / (d["ms_per_step"] * 2e-3)) < 1e-6 * d["value"]
+    assert d["gpu_launches"] >= 2 * 2  # measurement pre-pass + filter kernel per step
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 52 * 8192 * 8
+    r = d["roofline"]
+    assert r["bound"] == "fma" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["peak"] > 10
+    assert d["status_nonzero_trajectories"] == 0 and d["clocks"]["sm_mhz"] is not None
