@@ -10,13 +10,16 @@
 //   * Three channel groups, each single-buffered and refilled for step t+1 the moment the warp has consumed
 //     step t's copy, so the copy has most of a filter step (several microseconds) to land:
 //         G0 = p[12] f[12]      read at the top of the step (mean model)        -> refilled right away
-//         G1 = z[10]            read one by one as the measurements are folded  -> refilled after the last fold
-//         G2 = truth / nominal  label streams of the summary, read at the end   -> refilled right away
+//              (+ the 3 reference body angles of the predict_mpc covariance model in the kMpc instantiations)
+//         G1 = z[10]            read one by one as the measurements are folded  -> refilled before the last fold
+//         G2 = truth / nominal  label streams of the summary, read inside the last fold -> refilled after it
 //   * Inputs are consumed straight from shared memory (conflict-free: consecutive threads, consecutive words);
 //     nothing but x, P and the next step's rotation matrix stays live across the step.
 //   * Latency of the two long dependent chains is hidden behind the independent rank-1 FMAs: the reciprocal of
 //     the NEXT pivot is started as soon as that pivot's entry has been updated, and the sin/cos of the NEXT
-//     step's attitude are started as soon as the last state update is done.
+//     step's attitude - and the summary's running error sums - are started as soon as the last state update is done.
+//   * Template variants instead of branches in the time loop (kSummary, kOut, kMpc): a taken branch over an unused block
+//     costs an instruction-fetch bubble at its target, ~10 % of a lone warp's time before they were compiled out.
 //   * Instantiated for double, float and F2 (kf_arith.cuh): F2 packs TWO FP32 trajectories into one thread and runs
 //     the recursion on FFMA2 / FADD2 / FMUL2, halving the issue slots per trajectory-step; its tiles are [C] x 64.
 //   * z comes from the measurement pre-pass (optistate_kf_measure): it is state-independent and, with shared
