@@ -119,7 +119,7 @@ def kf_batch(
     algo: str = "auto", cov_model: str = "predict", q_kind=None, r_kind=None, p0_kind=None,
     dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
     gravity: float = INITIAL_PARAMS.GRAVITY, device=None, out: Optional[Dict[str, torch.Tensor]] = None,
-    summary_peers=None,
+    summary_peers=None, p0_is_symmetric: Optional[bool] = None,
 ) -> KfBatchResult:
     """Runs the Kalman filter over N trajectories x T steps on the current CUDA device.
 
@@ -131,6 +131,8 @@ def kf_batch(
     (k_gain), nis_steps, P_ckpt (p_checkpoints, needs ckpt_every), x_final, P_final, final (= both), K_final, summary.
     algo: "auto" | "sequential" | "joint" (see include/optistate_kf.h).  cov_model: "predict" | "mpc".
     out: optional preallocated output tensors by canonical name.
+    p0_is_symmetric: skips the (synchronising) symmetry test of a dense P0 when the caller knows the answer, e.g. when P0
+    is the P_final of a previous sequential call.
     summary_peers: an optistate_b200.peer.PeerSummary - the summary is then written into this rank's columns of the
     job-wide [52, n_total] array on EVERY GPU of the box by the filter kernel itself (fused all-gather over NVLink peer
     stores); `result.summary` is the local column block, `summary_peers.tensor` the gathered array once
@@ -170,7 +172,7 @@ def kf_batch(
         tensors["P0"], pk = _noise(P0, 12, N, "P0", dtype, device, p0_kind)
         if pk in (nv.MAT_DENSE, nv.MAT_DENSE_PER):
             m = tensors["P0"].reshape(12, 12, -1)
-            p0_symmetric = bool(torch.equal(m, m.transpose(0, 1)))
+            p0_symmetric = bool(torch.equal(m, m.transpose(0, 1))) if p0_is_symmetric is None else bool(p0_is_symmetric)
     if stream_index is not None:
         tensors["stream_index"] = _as_device(stream_index, torch.int32, device).reshape(N)
 

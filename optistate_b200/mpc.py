@@ -77,12 +77,20 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     fs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
     mst = torch.empty((T, N), dtype=torch.int32, device=device)
     fst = torch.zeros(N, dtype=torch.int32, device=device)
+    # everything that would make a step synchronise with the host is settled once: diagonal noise as device vectors, the
+    # bound on the legs out of swing over all steps, and the symmetry of P (the packed-symmetric filter keeps it exactly)
+    q_d = torch.diagonal(_as_device(INITIAL_PARAMS.Q if Q is None else Q, torch.float64, device).reshape(12, 12)).contiguous() \
+        if Q is None or np.shape(Q) == (12, 12) else _as_device(Q, torch.float64, device)
+    r_d = torch.diagonal(_as_device(INITIAL_PARAMS.R if R is None else R, torch.float64, device).reshape(10, 10)).contiguous() \
+        if R is None or np.shape(R) == (10, 10) else _as_device(R, torch.float64, device)
+    if "max_free_legs" not in kw:
+        kw["max_free_legs"] = max(1, int((contact != 0).sum(dim=1).max())) if T * N > 0 else 4
     for t in range(T):
         forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **kw)
         fs[t], mst[t] = forces[0], st
-        res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=Q, R=R, n_traj=N,
-                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"),
-                       p0_kind=None if Pm is None else nv.MAT_DENSE_PER)
+        res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=q_d, R=r_d, n_traj=N,
+                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"), algo="sequential",
+                       p0_kind=None if Pm is None else nv.MAT_DENSE_PER, p0_is_symmetric=True)
         x, Pm = res.x_final, res.P_final
         xs[t] = x
         fst |= res.status
