@@ -83,24 +83,28 @@ __device__ __forceinline__ void lane_set(double &a, int, double s) { a = s; }
 __device__ __forceinline__ void lane_set(float &a, int, float s) { a = s; }
 __device__ __forceinline__ void lane_set(F2 &a, int l, float s) { if (l == 0) a.v.x = s; else a.v.y = s; }
 
-// largest |component| over lanes (trunc pre-test)
-__device__ __forceinline__ double absmax_lanes(double a) { return fabs(a); }
-__device__ __forceinline__ float absmax_lanes(float a) { return fabsf(a); }
-__device__ __forceinline__ float absmax_lanes(F2 a) { return fmaxf(fabsf(a.v.x), fabsf(a.v.y)); }
+// Magnitude of a value as an ordered integer (high word of a double, the word of a float, sign cleared; the larger of the
+// two lanes of an F2): |a| >= |b| <=> abs_bits(a) >= abs_bits(b) up to the low word of a double.  The status checks and
+// the trunc pre-test compare these on the integer pipe instead of spending FP64-pipe slots on DSETP.
+__device__ __forceinline__ int abs_bits(double a) { return __double2hiint(a) & 0x7fffffff; }
+__device__ __forceinline__ int abs_bits(float a) { return __float_as_int(a) & 0x7fffffff; }
+__device__ __forceinline__ int abs_bits(F2 a) { return max(abs_bits(a.v.x), abs_bits(a.v.y)); }
 
-// pivot check: s must be positive and finite (OPTI_KF_ST_NOT_PD otherwise), per lane
-template <typename S> __device__ __forceinline__ bool bad_pivot_scalar(S s) { return !(s > S(0)) || !(s < S(3e38)); }
+// pivot check: s must be positive and finite (OPTI_KF_ST_NOT_PD otherwise), per lane.  On the bit pattern: the (high) word
+// of a positive finite number lies in [1, 0x7fefffff] (double) / [1, 0x7f7fffff] (float).
+__device__ __forceinline__ bool bad_pivot_scalar(double s) { return (unsigned)(__double2hiint(s) - 1) >= 0x7fefffffu; }
+__device__ __forceinline__ bool bad_pivot_scalar(float s) { return (unsigned)(__float_as_int(s) - 1) >= 0x7f7fffffu; }
 __device__ __forceinline__ void note_bad_pivot(double s, uint32_t (&st)[1], uint32_t bit) { if (bad_pivot_scalar(s)) st[0] |= bit; }
 __device__ __forceinline__ void note_bad_pivot(float s, uint32_t (&st)[1], uint32_t bit) { if (bad_pivot_scalar(s)) st[0] |= bit; }
 __device__ __forceinline__ void note_bad_pivot(F2 s, uint32_t (&st)[2], uint32_t bit) {
     if (bad_pivot_scalar(s.v.x)) st[0] |= bit;
     if (bad_pivot_scalar(s.v.y)) st[1] |= bit;
 }
-__device__ __forceinline__ void note_nonfinite(double x, uint32_t (&st)[1], uint32_t bit) { if (!isfinite(x)) st[0] |= bit; }
-__device__ __forceinline__ void note_nonfinite(float x, uint32_t (&st)[1], uint32_t bit) { if (!isfinite(x)) st[0] |= bit; }
+__device__ __forceinline__ void note_nonfinite(double x, uint32_t (&st)[1], uint32_t bit) { if (abs_bits(x) >= 0x7ff00000) st[0] |= bit; }
+__device__ __forceinline__ void note_nonfinite(float x, uint32_t (&st)[1], uint32_t bit) { if (abs_bits(x) >= 0x7f800000) st[0] |= bit; }
 __device__ __forceinline__ void note_nonfinite(F2 x, uint32_t (&st)[2], uint32_t bit) {
-    if (!isfinite(x.v.x)) st[0] |= bit;
-    if (!isfinite(x.v.y)) st[1] |= bit;
+    if (abs_bits(x.v.x) >= 0x7f800000) st[0] |= bit;
+    if (abs_bits(x.v.y) >= 0x7f800000) st[1] |= bit;
 }
 
 // ---- running sums of the summary ---------------------------------------------------------------------------------

@@ -128,9 +128,6 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
         if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
             kgain = gain_trace(P, r, nt);
         }
-#pragma unroll
-        for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
-
         if (prm.x_steps) {
 #pragma unroll
             for (int c = 0; c < NX; ++c) st_stream(prm.x_steps + (t * NX + c) * N + i, x[c]);
@@ -158,6 +155,8 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
         }
     }
 
+#pragma unroll
+    for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);  // absorbing: see kf_seq_tma.cuh
     if (prm.x_final) {
 #pragma unroll
         for (int c = 0; c < NX; ++c) prm.x_final[c * N + i] = x[c];

@@ -213,10 +213,10 @@ __device__ __forceinline__ Real gain_trace(const Real (&P)[NP], const Real *r, i
 template <typename Real>
 __device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {
     using S = typename Lanes<Real>::scalar;
-    S m = S(0);
+    int m = 0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) m = max_(m, absmax_lanes(R[k]));
-    return m >= (sizeof(S) == 8 ? S(1) : S(1.0f - 9.5367431640625e-7f));
+    for (int k = 0; k < 9; ++k) m = max(m, abs_bits(R[k]));
+    return m >= (sizeof(S) == 8 ? 0x3ff00000 : 0x3f7ffff0);  // |entry| >= 1 (double) / >= 1 - 2^-20 (float)
 }
 
 // Mean model with the rotation of the prior attitude supplied by the caller (see propagate_mean in kf_common.cuh).

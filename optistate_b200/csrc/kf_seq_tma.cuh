@@ -331,8 +331,6 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         });
 
         ymax = max_(ymax, nis);
-#pragma unroll
-        for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
 
         if constexpr (kOut != 0) {
             ptrace = trace_of(P);
@@ -366,6 +364,10 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         }
     }
 
+    // A non-finite state is absorbing (NaN and Inf - Inf propagate through every later predict and update, nothing divides by
+    // the state), so testing the final state flags the same trajectories as testing after every step.
+#pragma unroll
+    for (int c = 0; c < NX; ++c) note_nonfinite(x[c], status, OPTI_KF_ST_NONFINITE);
     if (!active) return;
     if (prm.x_final) {
 #pragma unroll

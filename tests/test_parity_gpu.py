@@ -203,6 +203,20 @@ def test_status_bits_all_swing_and_not_pd():
         assert (res.status.cpu().numpy() & 1).all()
 
 
+def test_status_bit_nonfinite_is_raised_by_every_kernel():
+    """A NaN measurement at one step of one stream poisons that trajectory's state for good: bit 2 for it, none for the others."""
+    st = make_streams(range(64), 40)
+    st["imu"][7, 4, 9] = np.nan
+    cases_ = [dict(), dict(stream_index=torch.arange(64, dtype=torch.int32)), dict(algo="joint"), dict(dtype=torch.float32),
+              dict(outputs=("x_steps",)), dict(outputs=("summary",), truth=st["truth"])]
+    for kw in cases_:
+        kw = dict(dict(outputs=("x_final",)), **kw)
+        res = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
+        status = res.status.cpu().numpy()
+        assert status[9] & 2, kw
+        assert not (np.delete(status, 9) & 2).any(), kw
+
+
 def test_summary_rows():
     from optistate_b200.batch import SUMMARY_FIELDS
 
