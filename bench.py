@@ -44,7 +44,7 @@ FLOPS_ALGORITHMIC = 6800.0  # per trajectory-step, reference ope
 FLOPS_EXECUTED = {"f64": 2 * 1135 + 321 + 99, "f32": (2 * 2 * 1051 + 2 * 302 + 2 * 85 + 2 * 54 + 30 + 8) / 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the ncu
 # captures summarised in profiles/r1_ncu_bench_kernel_*_metrics.txt; None for any other workload shape
-TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 2.645e9 + 0.435e9, ("f32", 1 << 20, 1000, 1024): 1.169e9 + 0.214e9}
+TRAFFIC_BYTES = {("f64", 1 << 20, 1000, 1024): 2.724e9 + 0.433e9, ("f32", 1 << 20, 1000, 1024): 1.230e9 + 0.212e9}
 # algorithmic bytes of one launch: every base-stream channel read once (p, f, z, two label streams = 58 scalars per
 # stream-step) + 22 noise scalars in and 52 summary scalars out per trajectory
 def algorithmic_bytes(a, esz):
