@@ -222,8 +222,8 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *desc, void *cuda_strea
  * set up by kalman_filter.py:64-77,140-152), batched.  One strictly convex QP per problem: 5 stages x 4 legs x 3 force
  * components; swing legs (contact == 0) carry no force, stance legs (contact == 1) satisfy fz <= fz_max, |fx| <= mu fz,
  * |fy| <= mu fz.  The reference solves it with CasADi + qpOASES, which are not available offline and no reference test pins
- * a force vector: parity is anchored on the uniqueness of the minimiser (tests check KKT optimality and an independent
- * active-set solve).  FP64 only. ---- */
+ * a force vector: the QP (objective and constraints) is pinned to the reference's own set-up code, the solver is anchored on
+ * the uniqueness of the minimiser (tests check KKT optimality and an independent active-set solve).  FP64 only. ---- */
 #define OPTI_KF_MPC_HORIZON 5
 enum { OPTI_KF_MPC_ST_IPM_LIMIT = 1,  /* interior-point phase stopped on its iteration cap or a pivot breakdown       */
        OPTI_KF_MPC_ST_UNPOLISHED = 2, /* active-set polish did not settle: the forces are the interior-point iterate

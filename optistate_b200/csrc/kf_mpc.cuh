@@ -7,8 +7,10 @@
 //       cost = sum_i (state_{i+1} - body_mpc[:, i+1])^T W (.) + u_i^T R u_i                        force_controller.py:95-104
 //       contact == 0: f = 0;  contact == 1: fz <= fz_max, |fx| <= mu fz, |fy| <= mu fz (=> fz >= 0);  other: free   :106-156
 //
-// The reference hands this to CasADi + qpOASES (an active-set solver), neither of which exists offline: PARITY UNPINNED.  The
-// QP is strictly convex (R > 0), so its minimiser is unique and any exact solver agrees with qpOASES to solver tolerance.
+// The reference hands this to CasADi + qpOASES (an active-set solver), neither of which exists offline.  The QP itself is
+// pinned to the reference (oracle/mpc_ref_shim.py evaluates the unmodified set-up code numerically; golden fixture
+// tests/golden/mpc_reference_qp.npz); the SOLVER is unpinned, but the QP is strictly convex (R > 0), so its minimiser is
+// unique and any exact solver agrees with qpOASES to solver tolerance.
 // Here: swing legs are left out of the unknowns (order n = 15 x legs not in swing), the condensed Hessian H (packed lower
 // triangle, <= 1,830 doubles) and gradient g are built in shared memory, a Mehrotra predictor-corrector interior-point
 // method brings the iterate to complementarity ~1e-9, and a polish phase (method of multipliers on the identified active

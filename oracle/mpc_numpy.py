@@ -9,9 +9,14 @@ NumPy restatement of the reference's convex force MPC, /root/reference/misc/forc
     cost = sum_i (state_{i+1} - body_mpc[:, i+1])^T W_i (.) + u_i^T R u_i,  W_i = Q (i < N-1), P (i = N-1)      :95-104
     swing leg (contact == 0): f = 0;  stance leg (contact == 1): 0 <= fz <= 150, |fx| <= mu fz, |fy| <= mu fz    :106-156
 
-PARITY UNPINNED: the reference solves this QP with CasADi 3.6.2 + qpOASES (environment.yml:25), neither of which is
-available offline, and no reference test or fixture holds a force vector.  What anchors this file instead:
-  * `rollout_cost` restates the reference's objective loop literally; `build_qp` (the condensed H, g) is checked against it;
+PARITY: the QP is PINNED to the reference, its SOLVER is unpinned.  The reference solves this QP with CasADi 3.6.2 +
+qpOASES (environment.yml:25), neither of which is available offline, and no reference test or fixture holds a force
+vector.  What anchors this file:
+  * oracle/mpc_ref_shim.py runs the UNMODIFIED StanceController.__init__ under a numeric stand-in for casadi, which makes
+    the reference's own code evaluate its objective and its subject_to constraints for given forces;
+    tests/golden/mpc_reference_qp.npz (oracle/gen_golden_mpc.py) holds 80 such evaluations, and `rollout_cost` / `build_qp` /
+    `constraints` below reproduce every one of them (cost to 1e-12, feasibility verdicts exactly, including forces that
+    break exactly one constraint);
   * the QP is strictly convex (R > 0), so its minimiser is unique: any correct solver returns qpOASES' answer up to solver
     tolerance.  `solve_ldp` (least-distance programming through NNLS, an active-set method - a different algorithm from
     the GPU's interior-point method) and `kkt_certificate` (solver-independent optimality check) are the checkers.

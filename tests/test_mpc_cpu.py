@@ -66,3 +66,55 @@ def test_mpc_descriptor_validation():
     d.struct_size -= 8
     assert lib.optistate_kf_mpc_forces(ctypes.byref(d), None) == -2
     assert lib.optistate_kf_mpc_forces(None, None) == -1
+
+
+def _oracle_verdict(f, x, ref, p, contact):
+    """(cost, feasible) of forces (12, 5) by the oracle's restatement."""
+    H, g, c0 = mpc.build_qp(x, ref, p)
+    A, b, pinned = mpc.constraints(contact)
+    u = np.asarray(f, float).T.reshape(-1)
+    feasible = bool((A @ u <= b).all() if A.shape[0] else True) and bool((u[pinned] == 0).all())
+    return mpc.rollout_cost(f, x, ref, p), 0.5 * u @ H @ u + g @ u + c0, feasible
+
+
+def test_oracle_qp_is_the_reference_stance_controller_golden():
+    """tests/golden/mpc_reference_qp.npz holds what the UNMODIFIED reference set-up code (StanceController.__init__,
+    force_controller.py:44-156, run numerically through oracle/mpc_ref_shim.py) evaluates for 80 force vectors: objective
+    value and whether every subject_to holds - including vectors that break exactly one constraint (fz = 150.5, |fx| =
+    0.61 fz, a swing force of 1e-3) next to their just-feasible twins.  The oracle's QP is that QP."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_reference_qp.npz"))
+    assert g["cost"].shape[0] == 80 and 20 < int(g["feasible"].sum()) < 60
+    for k in range(g["cost"].shape[0]):
+        rollout, condensed, feasible = _oracle_verdict(g["forces"][k], g["x"][k], g["body_ref"][k], g["p"][k], g["contact"][k])
+        assert abs(rollout - g["cost"][k]) <= 1e-12 * abs(g["cost"][k]), k
+        assert abs(condensed - g["cost"][k]) <= 1e-10 * abs(g["cost"][k]), k
+        assert feasible == bool(g["feasible"][k]), (k, g["contact"][k])
+
+
+def test_oracle_qp_against_the_live_reference_set_up():
+    from oracle import mpc_ref_shim as shim
+
+    if not shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    rng = np.random.default_rng(11)
+    for contact in ([1, 0, 0, 1], [1, 1, 1, 1], [0, 1, 0, 0]):
+        x, ref, p = mpc_cases.problem(rng, lateral=0.5)
+        for scale in (1.0, 40.0):
+            f = scale * rng.standard_normal((12, 5))
+            cost, feasible = shim.evaluate(f, x, ref, p, contact)
+            rollout, condensed, ofeas = _oracle_verdict(f, x, ref, p, contact)
+            assert abs(rollout - cost) <= 1e-12 * abs(cost) and abs(condensed - cost) <= 1e-10 * abs(cost) and ofeas == feasible
+        # the oracle's minimiser is feasible for the reference and no feasible perturbation of it has a lower reference cost
+        opt = mpc.solve(x, ref, p, contact)
+        inner = np.zeros((12, 5))
+        for l in range(4):
+            if contact[l] == 1:
+                inner[3 * l + 2] = 10.0
+        c_opt, _ = shim.evaluate(opt, x, ref, p, contact)
+        for _ in range(10):
+            d = rng.standard_normal((12, 5)) * (np.repeat(np.asarray(contact, float), 3)[:, None] == 1)
+            cand = opt + 1e-3 * (0.5 * (inner - opt) + 0.05 * d)   # moves into the interior of the feasible set
+            c, feas = shim.evaluate(cand, x, ref, p, contact)
+            assert feas and c >= c_opt - 1e-12 * abs(c_opt)
