@@ -8,7 +8,7 @@
 //       contact == 0: f = 0;  contact == 1: fz <= fz_max, |fx| <= mu fz, |fy| <= mu fz (=> fz >= 0);  other: free   :106-156
 //
 // The reference hands this to CasADi + qpOASES (an active-set solver), neither of which exists offline.  The QP itself is
-// pinned to the reference (oracle/mpc_ref_shim.py evaluates the unmodified set-up code numerically; golden fixture
+// pinned to the reference (the test infrastructure evaluates the unmodified set-up code numerically; golden fixture
 // tests/golden/mpc_reference_qp.npz); the SOLVER is unpinned, but the QP is strictly convex (R > 0), so its minimiser is
 // unique and any exact solver agrees with qpOASES to solver tolerance.
 // Here: swing legs are left out of the unknowns (order n = 15 x legs not in swing), the condensed Hessian H (packed lower
