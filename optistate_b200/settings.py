@@ -1,24 +1,23 @@
-"""Mirror of the reference's settings.INITIAL_PARAMS for the constants the filter reads
-(/root/reference/settings.py:2-31).  Same attribute names, same aliasing: P is the same object as Q
-(settings.py:31) and Kalman_Filter().x is the same object as STARTING_STATE (kalman_filter.py:10)."""
+"""The constants the filter reads, under the names the reference's drivers use (`settings.INITIAL_PARAMS`,
+/root/reference/settings.py:2-31) and with the same aliasing: `P` is the same object as `Q` (settings.py:31), and
+`Kalman_Filter().x` is the same object as `STARTING_STATE` (kalman_filter.py:10)."""
 import numpy as np
+
+_INERTIA_DIAGONAL_E9 = (55303643.08, 60119440.34, 105304340.05)  # body-frame xx, yy, zz in kg m^2 x 1e9
+_Q_DIAGONAL = [1e-2] * 4 + [1e-4] + [1e-2] * 6 + [1e-4]           # thx thy thz x | y | z wx wy wz vx vy | vz
+_R_DIAGONAL = [1e-2] * 10                                          # th_imu(3) z_odom w_imu(3) v_odom(3)
 
 
 class INITIAL_PARAMS:
-    DT_mpc = 0.01
-    DT = 0.01
-    ROBOT_HEIGHT = 0.28
-    ROBOT_MASS = 8.8
+    DT = DT_mpc = 1e-2                       # filter / MPC step in seconds
+    ROBOT_HEIGHT, ROBOT_MASS, GRAVITY = 0.28, 8.8, -9.81   # GRAVITY: kalman_filter.py:56
     KF_FREQUENCY = 500
-    DATA_CUTOFF_START = 430
-    DATA_CUTOFF_END = 4494
-    VISUALIZE_DATA_CONVERSION = False
-    Px = 55303643.08 / (10 ** 9)
-    Py = 60119440.34 / (10 ** 9)
-    Pz = 105304340.05 / (10 ** 9)
-    INERTIA_ROT = np.array([[Px, 0, 0], [0, Py, 0], [0, 0, Pz]])
-    STARTING_STATE = np.array([0.0, 0.0, 0.0, 0.0, 0.0, ROBOT_HEIGHT, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]).reshape(12, 1)
-    Q = np.diag([0.01, 0.01, 0.01, 0.01, 0.0001, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.0001])
-    R = np.diag([0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01])
+    DATA_CUTOFF_START, DATA_CUTOFF_END = 430, 4494
+    VISUALIZE_DATA_CONVERSION = False        # plotting is out of scope here
+    Px, Py, Pz = (v / 1e9 for v in _INERTIA_DIAGONAL_E9)
+    INERTIA_ROT = np.diag([Px, Py, Pz])
+    STARTING_STATE = np.zeros((12, 1))
+    STARTING_STATE[5, 0] = ROBOT_HEIGHT
+    Q = np.diag(np.asarray(_Q_DIAGONAL, dtype=float))
+    R = np.diag(np.asarray(_R_DIAGONAL, dtype=float))
     P = Q
-    GRAVITY = -9.81  # kalman_filter.py:56
