@@ -159,6 +159,11 @@ def test_product_path_fails_loudly_without_a_gpu():
     kf = Kalman_Filter()  # construction is host-only, like the reference's
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         kf.update()
+    from optistate_b200 import mpc_forces
+    from optistate_b200.synth import make_mpc_problems
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mpc_forces(*make_mpc_problems(4))
 
 
 def test_product_package_never_imports_the_oracle():
