@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define OPTISTATE_KF_ABI_VERSION 2
+#define OPTISTATE_KF_ABI_VERSION 3
 
 #define OPTI_KF_NX 12 /* states  [thx thy thz | x y z | wx wy wz | vx vy vz]   kalman_filter.py:9  */
 #define OPTI_KF_NZ 10 /* measurements [th_imu(3) z_odom w_imu(3) v_odom(3)]    kalman_filter.py:11 */
@@ -75,6 +75,15 @@ enum {
     OPTI_KF_MAT_DENSE = 3,      /* [n*n]      one dense row-major matrix shared                */
     OPTI_KF_MAT_DENSE_PER = 4   /* [n*n][N]   one dense row-major matrix per trajectory        */
 };
+
+/* flags (OptiKfDesc.flags)
+ *   The predict() model decouples: F_d = I + dt F mixes attitude only with body rate (F[0:3,6:9] = R^T) and each position
+ *   only with the velocity of the same axis (F[3:6,9:12] = I, kalman_filter.py:45-48); H selects, Q and R are diagonal.  With
+ *   a P0 that has no entries across the groups {th, w}, {x, vx}, {y, vy}, {z, vz} - P0 = Q as in settings.py:31, or any
+ *   diagonal P0 - every cross-group entry of P stays an exact zero in the reference as well, and the SEQUENTIAL kernels drop
+ *   the multiplications by those zeros (30 packed scalars instead of 78; bit-identical results).  Diagonal P0 kinds select
+ *   this automatically; P0_DECOUPLED lets the caller vouch for a dense P0; FULL_COVARIANCE turns it off (tests, comparison). */
+enum { OPTI_KF_FLAG_P0_DECOUPLED = 1, OPTI_KF_FLAG_FULL_COVARIANCE = 2 };
 
 /* status[i] bits */
 enum {
@@ -155,7 +164,7 @@ typedef struct OptiKfDesc {
        a barrier of its own (one NCCL barrier in optistate_b200.distributed). */
     int64_t summary_ld;
     int32_t n_summary_peers; /* 0 .. OPTI_KF_MAX_PEERS */
-    int32_t reserved0;
+    int32_t flags;           /* OPTI_KF_FLAG_* */
     void *summary_peers[OPTI_KF_MAX_PEERS];
 } OptiKfDesc;
 

@@ -33,6 +33,10 @@ _OUT_SHAPES = {
 _ALGOS = {"auto": nv.ALGO_AUTO, "joint": nv.ALGO_JOINT, "sequential": nv.ALGO_SEQUENTIAL}
 _ALGO_NAMES = {nv.ALGO_JOINT: "joint", nv.ALGO_SEQUENTIAL: "sequential"}
 
+# decoupled groups of the predict() model (include/optistate_kf.h OPTI_KF_FLAG_*): {th, w}, {x, vx}, {y, vy}, {z, vz}
+_GROUP = torch.tensor([0, 0, 0, 1, 2, 3, 0, 0, 0, 1, 2, 3])
+_CROSS_GROUP = _GROUP[:, None] != _GROUP[None, :]
+
 SUMMARY_FIELDS = {
     "x_final": slice(0, 12), "p_diag": slice(12, 24), "rmse_truth": slice(24, 36), "rms_dev_nominal": slice(36, 48),
     "mean_nis": 48, "p_trace": 49, "k_gain": 50, "max_nis_sqrt": 51,
@@ -119,7 +123,7 @@ def kf_batch(
     algo: str = "auto", cov_model: str = "predict", q_kind=None, r_kind=None, p0_kind=None,
     dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
     gravity: float = INITIAL_PARAMS.GRAVITY, device=None, out: Optional[Dict[str, torch.Tensor]] = None,
-    summary_peers=None, p0_is_symmetric: Optional[bool] = None,
+    summary_peers=None, p0_is_symmetric: Optional[bool] = None, structure: str = "auto",
 ) -> KfBatchResult:
     """Runs the Kalman filter over N trajectories x T steps on the current CUDA device.
 
@@ -133,6 +137,11 @@ def kf_batch(
     out: optional preallocated output tensors by canonical name.
     p0_is_symmetric: skips the (synchronising) symmetry test of a dense P0 when the caller knows the answer, e.g. when P0
     is the P_final of a previous sequential call.
+    structure: "auto" | "full" - the sequential kernels exploit that predict()'s F_d only couples attitude with body rate
+    and each position with the velocity of its axis, so with a P0 without entries across those groups (None, diagonal, or
+    a dense P0 whose cross-group entries are all zero - checked here) the cross-group entries of P are exact zeros at every
+    step, in the reference too, and are neither stored nor multiplied (bit-identical results, less than half the
+    arithmetic).  "full" keeps all 78 packed entries regardless (tests, comparison).
     summary_peers: an optistate_b200.peer.PeerSummary - the summary is then written into this rank's columns of the
     job-wide [52, n_total] array on EVERY GPU of the box by the filter kernel itself (fused all-gather over NVLink peer
     stores); `result.summary` is the local column block, `summary_peers.tensor` the gathered array once
@@ -168,11 +177,18 @@ def kf_batch(
     tensors["R"], rk = _noise(INITIAL_PARAMS.R if R is None else R, 10, N, "R", dtype, device, r_kind)
     pk = nv.MAT_NONE
     p0_symmetric = True
+    if structure not in ("auto", "full"):
+        raise ValueError("structure must be 'auto' or 'full'")
+    flags = nv.FLAG_FULL_COVARIANCE if structure == "full" else 0
     if P0 is not None:
         tensors["P0"], pk = _noise(P0, 12, N, "P0", dtype, device, p0_kind)
         if pk in (nv.MAT_DENSE, nv.MAT_DENSE_PER):
             m = tensors["P0"].reshape(12, 12, -1)
             p0_symmetric = bool(torch.equal(m, m.transpose(0, 1))) if p0_is_symmetric is None else bool(p0_is_symmetric)
+            if structure == "auto" and p0_is_symmetric is None and p0_symmetric and cov_model != "mpc":
+                # (the test synchronises, like the symmetry test; callers that pass p0_is_symmetric skip both)
+                if not bool(torch.count_nonzero(m[_CROSS_GROUP.to(device)])):
+                    flags |= nv.FLAG_P0_DECOUPLED
     if stream_index is not None:
         tensors["stream_index"] = _as_device(stream_index, torch.int32, device).reshape(N)
 
@@ -201,7 +217,7 @@ def kf_batch(
     cfg = dict(dtype=nv.F64 if dtype == torch.float64 else nv.F32, algo=_ALGOS[algo],
                cov_model=nv.COV_MPC if cov_model == "mpc" else nv.COV_PREDICT, phases=phases, n_traj=N, n_steps=T,
                n_streams=S, stream_offset=int(stream_offset), x0_per_traj=int(x0_t.dim() == 2), p0_kind=pk, q_kind=qk,
-               r_kind=rk, ckpt_every=int(ckpt_every), want_K=int("K_final" in want))
+               r_kind=rk, ckpt_every=int(ckpt_every), want_K=int("K_final" in want), flags=flags)
     if summary_peers is not None and "summary" in want:
         cfg.update(summary_peers.cfg())
     if cfg["algo"] == nv.ALGO_AUTO:

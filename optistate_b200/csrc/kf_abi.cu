@@ -38,6 +38,7 @@ int validate(const OptiKfDesc *d) {
     if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     if (d->summary_ld < 0 || (d->summary_ld > 0 && d->summary_ld < d->n_traj)) return OPTI_KF_E_SHAPE;
     if (d->n_summary_peers < 0 || d->n_summary_peers > OPTI_KF_MAX_PEERS) return OPTI_KF_E_SHAPE;
+    if (d->flags & ~(OPTI_KF_FLAG_P0_DECOUPLED | OPTI_KF_FLAG_FULL_COVARIANCE)) return OPTI_KF_E_SHAPE;
     for (int k = 0; k < d->n_summary_peers; ++k)
         if (d->summary && !d->summary_peers[k]) return OPTI_KF_E_NULL;
     return OPTI_KF_OK;
@@ -64,6 +65,9 @@ okf::Params<Real> make_params(const OptiKfDesc *d) {
     std::memset(&p, 0, sizeof p);
     p.N = d->n_traj; p.T = d->n_steps; p.S = d->n_streams; p.stream_offset = d->stream_offset;
     p.phases = d->phases; p.cov_model = d->cov_model;
+    // decoupled groups (kf_seq_core.cuh): predict() model with a P0 that has no cross-group entries
+    const bool p0_groups = d->p0_kind == OPTI_KF_MAT_NONE || is_diag_kind(d->p0_kind) || (d->flags & OPTI_KF_FLAG_P0_DECOUPLED);
+    p.block = (d->cov_model == OPTI_KF_COV_PREDICT && p0_groups && !(d->flags & OPTI_KF_FLAG_FULL_COVARIANCE)) ? 1 : 0;
     p.dt = (Real)d->dt;
     p.dt_over_m = (Real)((1.0 / d->mass) * d->dt);  // B*dt with B = 1/m (force_controller.py:246-247,289)
     p.dt_g = (Real)(d->dt * d->gravity);
@@ -135,16 +139,20 @@ bool packed_pair_ok(const OptiKfDesc *d) {
     return true;
 }
 
+template <typename Real>
+int launch_streamed_t(const OptiKfDesc *d, const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    if (p.block) return d->summary ? okf::launch_seq_tma<Real, true, true>(p, stream) : okf::launch_seq_tma<Real, false, true>(p, stream);
+    return d->summary ? okf::launch_seq_tma<Real, true, false>(p, stream) : okf::launch_seq_tma<Real, false, false>(p, stream);
+}
 template <typename Scalar>
 int launch_streamed(const OptiKfDesc *d, const okf::Params<Scalar> &p, cudaStream_t stream);
 template <>
 int launch_streamed<double>(const OptiKfDesc *d, const okf::Params<double> &p, cudaStream_t stream) {
-    return d->summary ? okf::launch_seq_tma<double, true>(p, stream) : okf::launch_seq_tma<double, false>(p, stream);
+    return launch_streamed_t<double>(d, p, stream);
 }
 template <>
 int launch_streamed<float>(const OptiKfDesc *d, const okf::Params<float> &p, cudaStream_t stream) {
-    if (packed_pair_ok(d)) return d->summary ? okf::launch_seq_tma<okf::F2, true>(p, stream) : okf::launch_seq_tma<okf::F2, false>(p, stream);
-    return d->summary ? okf::launch_seq_tma<float, true>(p, stream) : okf::launch_seq_tma<float, false>(p, stream);
+    return packed_pair_ok(d) ? launch_streamed_t<okf::F2>(d, p, stream) : launch_streamed_t<float>(d, p, stream);
 }
 
 template <typename Real>

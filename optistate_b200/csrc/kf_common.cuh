@@ -20,6 +20,7 @@ template <typename Real>
 struct Params {
     long long N, T, S, stream_offset;
     int phases, cov_model;
+    int block;  // 1: P has the decoupled group structure (OPTI_KF_FLAG_*; kBlock kernels, kf_seq_core.cuh)
     Real dt, dt_over_m, dt_g, inv_inertia[3];
     const Real *imu, *p, *dp, *contact, *f, *z_in, *body_ref, *truth, *nominal;
     const int32_t *stream_index;

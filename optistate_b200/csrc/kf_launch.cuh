@@ -9,10 +9,10 @@
 namespace okf {
 
 // Streamed SEQUENTIAL kernel (kf_seq_tma.cuh) for Real = double | float | F2 (two FP32 trajectories per thread), with
-// (kSummary) or without the per-trajectory summary.  Picks the instantiation from the descriptor (per-step outputs,
+// (kSummary) or without the per-trajectory summary, on the full packed P or its decoupled groups (kBlock, Params.block).  Picks the instantiation from the descriptor (per-step outputs,
 // covariance model).  Returns OPTI_KF_OK, OPTI_KF_E_CUDA, or +1 when the tensor maps could not be built (the caller then
 // falls back to the direct-load kernel).
-template <typename Real, bool kSummary>
+template <typename Real, bool kSummary, bool kBlock>
 int launch_seq_tma(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream);
 
 // Direct-load SEQUENTIAL kernel (kf_seq.cuh).

@@ -10,7 +10,7 @@ namespace okf {
 
 constexpr int SEQ_NOISE_ROWS = 22;  // shared memory rows per thread: q[12] r[10]
 
-template <typename Real, bool kSummary, bool kMpc>
+template <typename Real, bool kSummary, bool kMpc, bool kBlock = false>
 __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Params<Real> prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Real *noise = reinterpret_cast<Real *>(smem_raw);  // [SEQ_NOISE_ROWS][blockDim.x]
@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
     for (int a = 0; a < NX; ++a)
 #pragma unroll
         for (int b = 0; b <= a; ++b) {
-            Real v;
-            switch (prm.p0_kind) {
+            Real v = Real(0);
+            if (cpl<kBlock>(a, b)) switch (prm.p0_kind) {  // structural zeros are never loaded
                 case OPTI_KF_MAT_NONE: v = (a == b) ? q[a * nt] : Real(0); break;
                 case OPTI_KF_MAT_DIAG: v = (a == b) ? prm.P0[a] : Real(0); break;
                 case OPTI_KF_MAT_DIAG_PER: v = (a == b) ? prm.P0[a * N + i] : Real(0); break;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
                 for (int k = 0; k < 3; ++k) E[3 * a + k] = exp_minus_one(prm.dt * Rb[3 * k + a]);
             cov_predict_mpc_sym(P, E, exp_minus_one(prm.dt), q, nt);
         } else {
-            cov_predict_sym(P, Rm, prm.dt, q, nt);
+            cov_predict_sym<kBlock>(P, Rm, prm.dt, q, nt);
         }
 
         Real nis = Real(0), inv, inv_n;
@@ -107,16 +107,16 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
             inv = rcp_(s0);
         }
         auto nothing = [] {};
-        fold_pipelined<0>(P, x, z[0], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<1>(P, x, z[1], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<2>(P, x, z[2], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<3>(P, x, z[3], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<4>(P, x, z[4], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<5>(P, x, z[5], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<6>(P, x, z[6], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<7>(P, x, z[7], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<8>(P, x, z[8], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<9>(P, x, z[9], r[9 * nt], r[9 * nt], inv, inv_n, nis, status, [&] {
+        fold_pipelined<0, kBlock>(P, x, z[0], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<1, kBlock>(P, x, z[1], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<2, kBlock>(P, x, z[2], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<3, kBlock>(P, x, z[3], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<4, kBlock>(P, x, z[4], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<5, kBlock>(P, x, z[5], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<6, kBlock>(P, x, z[6], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<7, kBlock>(P, x, z[7], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<8, kBlock>(P, x, z[8], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<9, kBlock>(P, x, z[9], r[9 * nt], r[9 * nt], inv, inv_n, nis, status, [&] {
             rot_zyx(x[0], x[1], x[2], Rm);  // next step's rotation, started underneath the last rank-1 update
             any_trunc = may_truncate(Rm);
         });
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
 #pragma unroll
         for (int c = 0; c < NX; ++c) ptrace += P[tri(c, c)];
         if (prm.k_gain_steps != nullptr || (last && prm.summary != nullptr)) {
-            kgain = gain_trace(P, r, nt);
+            kgain = gain_trace<kBlock>(P, r, nt);
         }
         if (prm.x_steps) {
 #pragma unroll
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
 #pragma unroll
             for (int a = 0; a < NX; ++a)
 #pragma unroll
-                for (int b = 0; b < NX; ++b) dst[(long long)(a * NX + b) * N] = P[tri(a, b)];
+                for (int b = 0; b < NX; ++b) dst[(long long)(a * NX + b) * N] = cpl<kBlock>(a, b) ? P[tri(a, b)] : Real(0);
         }
     }
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
 #pragma unroll
         for (int a = 0; a < NX; ++a)
 #pragma unroll
-            for (int b = 0; b < NX; ++b) prm.P_final[(long long)(a * NX + b) * N + i] = P[tri(a, b)];
+            for (int b = 0; b < NX; ++b) prm.P_final[(long long)(a * NX + b) * N + i] = cpl<kBlock>(a, b) ? P[tri(a, b)] : Real(0);
     }
     if (kSummary && prm.summary) {
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) kf_seq_kernel(const __grid_constant__ Par
         st_summary(prm, 50, i, kgain);
         st_summary(prm, 51, i, (Real)sqrt((double)ymax));
     }
-    if (prm.status) prm.status[i] = status[0];
+    if (prm.status) prm.status[i] = status[0] | (prm.stream_status ? prm.stream_status[s] : 0u);  // pre-pass flags (ALL_SWING) of this stream
 }
 
 }  // namespace okf

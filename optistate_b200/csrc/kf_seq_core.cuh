@@ -12,6 +12,16 @@
 //     column times r/s, so the old column stays in place until the end and is never copied.
 //     K_gain = sum_i K[i][i] follows from the identity K = P'[:, sel] R^-1, NIS from sum_k y_k^2 / s_k.
 //   * Independent trajectories => no shuffles, no shared-memory traffic in the recursion, no redundant work.
+//   * kBlock variants exploit the DECOUPLING of this particular model.  F_d = I + dt F couples only attitude <-> body rate
+//     (F[0:3,6:9] = R^T) and position <-> velocity axis by axis (F[3:6,9:12] = I, kalman_filter.py:45-48), H is a selection and
+//     Q, R are diagonal, so the state splits into four groups that never mix in the covariance recursion:
+//         G0 = {th_x th_y th_z w_x w_y w_z} (6x6),  G1 = {x, v_x},  G2 = {y, v_y},  G3 = {z, v_z}  (2x2 each).
+//     If P0 has no entries across groups (P0 = Q as settings.py:31 has it, or any diagonal P0) every cross-group entry of P is
+//     an exact floating-point zero at every step of the REFERENCE too (a sum of products with one factor exactly zero; the
+//     pivoted LU of a block-structured S never fills a cross entry), so dropping the terms that multiply those zeros changes
+//     no bit of any other entry: 30 packed scalars instead of 78, a rank-1 update of 15 (or 1) FMAs instead of 66.  The kBlock
+//     kernels are therefore bit-identical to the full ones on such inputs (tests/test_parity_gpu.py) - they skip multiplications
+//     by structural zeros, which SURVEY 8(d) says never to count.  predict_mpc's element-wise exp makes F_d dense: no kBlock there.
 #pragma once
 
 #include "kf_common.cuh"
@@ -21,9 +31,14 @@ namespace okf {
 __host__ __device__ constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 constexpr int NP = 78;
 
+// decoupled groups of the predict() model (see the header comment): attitude + body rate, and one (position, velocity) pair per axis
+__host__ __device__ constexpr int grp(int i) { return (i < 3 || (i >= 6 && i < 9)) ? 0 : 1 + (i % 3); }
+template <bool kBlock>
+__host__ __device__ constexpr bool cpl(int i, int j) { return !kBlock || grp(i) == grp(j); }
+
 // P <- F_d P F_d^T + diag(q), F_d = I + dt N, N[a,c] = R^T, N[b,d] = I   (blocks a=0..2 b=3..5 c=6..8 d=9..11)
 // Written with explicit fma_ so that double, float and the packed F2 type run the same operation sequence.
-template <typename Real, typename Scalar>
+template <bool kBlock = false, typename Real, typename Scalar>
 __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9], Scalar dt_s, const Real *q, int qs) {
     constexpr int a = 0, b = 3, c = 6, d = 9;
     const Real dt = Real(dt_s);
@@ -33,6 +48,7 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
 #pragma unroll
         for (int k = 0; k < 3; ++k) A[3 * i + k] = dt * R[3 * k + i];
         // W rows that feed P'[a,a], P'[b,a], P'[b,b] use the OLD c- and d-rows: do them first.
+        // (kBlock: an entry P[i][j] with cpl(i, j) false is a structural zero - neither read nor written)
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -45,31 +61,35 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) P[tri(b + i, a + j)] = fma_(dt, P[tri(d + i, a + j)], P[tri(b + i, a + j)]);
+        for (int j = 0; j < 3; ++j)
+            if (cpl<kBlock>(b + i, a + j)) P[tri(b + i, a + j)] = fma_(dt, P[tri(d + i, a + j)], P[tri(b + i, a + j)]);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + i, b + j)], P[tri(b + i, b + j)]);
+        for (int j = 0; j <= i; ++j)
+            if (cpl<kBlock>(b + i, b + j)) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + i, b + j)], P[tri(b + i, b + j)]);
         // P'[c,a] = P[c,a] + P[c,c] A^T ; P'[d,a] = P[d,a] + P[d,c] A^T ; P'[c,b] = P[c,b] + dt P[c,d] ; P'[d,b] = P[d,b] + dt P[d,d]
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            Real s = P[tri(c + i, a + j)], u = P[tri(d + i, a + j)];
+            Real s = P[tri(c + i, a + j)];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                s = fma_(P[tri(c + i, c + k)], A[3 * j + k], s);
-                u = fma_(P[tri(d + i, c + k)], A[3 * j + k], u);
-            }
+            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + i, c + k)], A[3 * j + k], s);
             P[tri(c + i, a + j)] = s;
-            P[tri(d + i, a + j)] = u;
+            if (cpl<kBlock>(d + i, a + j)) {
+                Real u = P[tri(d + i, a + j)];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) u = fma_(P[tri(d + i, c + k)], A[3 * j + k], u);
+                P[tri(d + i, a + j)] = u;
+            }
         }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            P[tri(c + i, b + j)] = fma_(dt, P[tri(d + j, c + i)], P[tri(c + i, b + j)]);
-            P[tri(d + i, b + j)] = fma_(dt, P[tri(d + i, d + j)], P[tri(d + i, b + j)]);
+            if (cpl<kBlock>(c + i, b + j)) P[tri(c + i, b + j)] = fma_(dt, P[tri(d + j, c + i)], P[tri(c + i, b + j)]);
+            if (cpl<kBlock>(d + i, b + j)) P[tri(d + i, b + j)] = fma_(dt, P[tri(d + i, d + j)], P[tri(d + i, b + j)]);
         }
         // second factor: + W[a,c] A^T, + W[b,c] A^T, + dt W[b,d], with W[.,c] = P'[c,.]^T and W[b,d] = P'[d,b]^T
 #pragma unroll
@@ -84,16 +104,18 @@ __device__ __forceinline__ void cov_predict_sym(Real (&P)[NP], const Real (&R)[9
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            Real s = P[tri(b + i, a + j)];
+        for (int j = 0; j < 3; ++j)
+            if (cpl<kBlock>(b + i, a + j)) {
+                Real s = P[tri(b + i, a + j)];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, b + i)], A[3 * j + k], s);
-            P[tri(b + i, a + j)] = s;
-        }
+                for (int k = 0; k < 3; ++k) s = fma_(P[tri(c + k, b + i)], A[3 * j + k], s);
+                P[tri(b + i, a + j)] = s;
+            }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + j, b + i)], P[tri(b + i, b + j)]);
+        for (int j = 0; j <= i; ++j)
+            if (cpl<kBlock>(b + i, b + j)) P[tri(b + i, b + j)] = fma_(dt, P[tri(d + j, b + i)], P[tri(b + i, b + j)]);
 #pragma unroll
     for (int i = 0; i < NX; ++i) P[tri(i, i)] += q[i * qs];
 }
@@ -164,15 +186,18 @@ __device__ __forceinline__ void cov_predict_mpc_sym(Real (&P)[NP], const Real (&
 // Measurement J folded in with the reciprocal of its pivot already available (`inv` = 1 / (P_kk + r_J)).  The entry
 // that becomes the NEXT pivot is updated first and its reciprocal started at once, so that chain (MUFU + Newton
 // steps) runs underneath the 65 remaining independent FMAs of this rank-1 update.  `mid` runs after the state update.
-template <int J, typename Real, int L, typename Mid>
+template <int J, bool kBlock = false, typename Real, int L, typename Mid>
 __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Real zj, Real rj, Real r_next, Real inv, Real &inv_next,
                                                Real &nis, uint32_t (&status)[L], Mid mid) {
     constexpr int k = sel(J);
     constexpr int kn = (J + 1 < NZ) ? sel(J + 1) : -1;
     if constexpr (kn >= 0) {
-        const Real wn = P[tri(kn, k)] * inv;
-        const Real pnn = fnma_(wn, P[tri(kn, k)], P[tri(kn, kn)]);
-        P[tri(kn, kn)] = pnn;
+        Real pnn = P[tri(kn, kn)];
+        if constexpr (cpl<kBlock>(kn, k)) {
+            const Real wn = P[tri(kn, k)] * inv;
+            pnn = fnma_(wn, P[tri(kn, k)], pnn);
+            P[tri(kn, kn)] = pnn;
+        }
         const Real s = pnn + r_next;
         note_bad_pivot(s, status, OPTI_KF_ST_NOT_PD);
         inv_next = rcp_(s);
@@ -181,31 +206,34 @@ __device__ __forceinline__ void fold_pipelined(Real (&P)[NP], Real (&x)[NX], Rea
     const Real g = inv * y;
     nis = fma_(y, g, nis);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = fma_(P[tri(i, k)], g, x[i]);
+    for (int i = 0; i < NX; ++i)
+        if (cpl<kBlock>(i, k)) x[i] = fma_(P[tri(i, k)], g, x[i]);
     mid();
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-        if (i == k) continue;
+        if (i == k || !cpl<kBlock>(i, k)) continue;
         const Real w = P[tri(i, k)] * inv;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            if (j == k || (i == kn && j == kn)) continue;
+            if (j == k || !cpl<kBlock>(j, k) || (i == kn && j == kn)) continue;
             P[tri(i, j)] = fnma_(w, P[tri(j, k)], P[tri(i, j)]);
         }
     }
     const Real cfac = rj * inv;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) P[tri(i, k)] *= cfac;
+    for (int i = 0; i < NX; ++i)
+        if (cpl<kBlock>(i, k)) P[tri(i, k)] *= cfac;
 }
 
 // K_gain of the reference (np.trace of the 12x10 gain): K = P'[:, sel] R^-1  =>  K[j][j] = P'[j][sel(j)] / r_j.  The ten
 // reciprocals are the straight-line rcp_ (<= 2 ulp), not IEEE divisions: each division carries a branch to a slow path, and
 // ten of those in a row cost a lone warp ~4,000 cycles per step (measured on the 1,024 x 10 k case with k_gain_steps on).
-template <typename Real>
+template <bool kBlock = false, typename Real>
 __device__ __forceinline__ Real gain_trace(const Real (&P)[NP], const Real *r, int stride) {
     Real g = Real(0);
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) g = fma_(P[tri(j, sel(j))], rcp_(r[j * stride]), g);
+    for (int j = 0; j < NZ; ++j)
+        if (cpl<kBlock>(j, sel(j))) g = fma_(P[tri(j, sel(j))], rcp_(r[j * stride]), g);
     return g;
 }
 

@@ -119,13 +119,32 @@ __device__ __forceinline__ void issue_g2(const TmaMaps &m, long long t, int s_wa
 // (x_model_steps, p_world_steps, z_steps, P_ckpt).  Blocks of outputs that are not wanted are compiled out instead of being
 // jumped over every step: the taken branches across them cost the lone warp of a scheduler ~10 % of its time in
 // instruction-fetch bubbles (ncu: stall_no_inst / stall_branch_resolving at the branch targets of the 35 KB loop body).
-template <typename Real, bool kSummary, int kOut, bool kMpc>
-__global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) ? 3 : 2) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
+// kBlock: the decoupled-group form of the covariance recursion (kf_seq_core.cuh): 30 live scalars of P instead of 78, which
+// leaves room for more resident warps (see tma_min_blocks).
+template <typename Real, bool kSummary, bool kBlock>
+__host__ __device__ constexpr int tma_min_blocks() {
+#ifdef OKF_BLK_MINB
+    if (kBlock) return OKF_BLK_MINB;
+#endif
+    if (kBlock) return (sizeof(Real) == 8 || kSummary) ? 3 : 4;  // the FP32 summary keeps 25 FP64 sums in registers
+    return (sizeof(Real) == 4 && !kSummary) ? 3 : 2;
+}
+template <typename Real, bool kSummary, bool kBlock>
+__host__ __device__ constexpr bool tma_acc_in_smem() {
+#ifdef OKF_BLK_ACC_SMEM
+    if (kBlock) return kSummary && sizeof(Real) == 8 && OKF_BLK_ACC_SMEM;
+#endif
+    return kSummary && sizeof(Real) == 8;
+}
+
+template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock = false>
+__global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kBlock>()) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
     using AccT = typename Acc<Real>::type;
     constexpr int L = Lanes<Real>::n;                     // trajectories per thread
-    constexpr bool kAccSmem = kSummary && sizeof(Real) == 8;  // double / F2: the 25 running sums do not fit next to P in registers
+    static_assert(!(kBlock && kMpc), "the element-wise exponential of predict_mpc couples every state");
+    constexpr bool kAccSmem = tma_acc_in_smem<Real, kSummary, kBlock>();  // double / F2 with the full P: the 25 running sums do not fit next to P in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int nt = TMA_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,8 +205,8 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
     for (int a = 0; a < NX; ++a)
 #pragma unroll
         for (int b = 0; b <= a; ++b) {
-            Real v;
-            switch (prm.p0_kind) {
+            Real v = Real(0);
+            if (cpl<kBlock>(a, b)) switch (prm.p0_kind) {  // structural zeros are never loaded
                 case OPTI_KF_MAT_NONE: v = (a == b) ? q[a * nt] : Real(0); break;
                 case OPTI_KF_MAT_DIAG: v = (a == b) ? Real(prm.P0[a]) : Real(0); break;
                 case OPTI_KF_MAT_DIAG_PER: v = (a == b) ? ld_traj(prm.P0, a * N + ic, Real()) : Real(0); break;
@@ -284,7 +303,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
         }
 
         if constexpr (kMpc) cov_predict_mpc_sym(P, E, e1_mpc, q, nt);
-        else cov_predict_sym(P, Rm, prm.dt, q, nt);
+        else cov_predict_sym<kBlock>(P, Rm, prm.dt, q, nt);
 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
         mbar_wait(&bars[1], par);
@@ -305,19 +324,19 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
             inv = rcp_(s);
         }
         auto nothing = [] {};
-        fold_pipelined<0>(P, x, z[0 * 32], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<1>(P, x, z[1 * 32], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<2>(P, x, z[2 * 32], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<3>(P, x, z[3 * 32], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<4>(P, x, z[4 * 32], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<5>(P, x, z[5 * 32], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<6>(P, x, z[6 * 32], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<7>(P, x, z[7 * 32], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
-        fold_pipelined<8>(P, x, z[8 * 32], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<0, kBlock>(P, x, z[0 * 32], r[0 * nt], r[1 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<1, kBlock>(P, x, z[1 * 32], r[1 * nt], r[2 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<2, kBlock>(P, x, z[2 * 32], r[2 * nt], r[3 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<3, kBlock>(P, x, z[3 * 32], r[3 * nt], r[4 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<4, kBlock>(P, x, z[4 * 32], r[4 * nt], r[5 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<5, kBlock>(P, x, z[5 * 32], r[5 * nt], r[6 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<6, kBlock>(P, x, z[6 * 32], r[6 * nt], r[7 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<7, kBlock>(P, x, z[7 * 32], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
+        fold_pipelined<8, kBlock>(P, x, z[8 * 32], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
         const Real z9 = z[9 * 32], r9 = r[9 * nt];
         __syncwarp();  // every lane has read its last measurement of this step: refill G1 for step t + 1
         if (more) issue_g1(maps, t + 1, s_warp, g1w, &bars[1], lane);
-        fold_pipelined<9>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
+        fold_pipelined<9, kBlock>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
             // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
             rot_zyx(x[0], x[1], x[2], Rm);
             any_trunc = may_truncate(Rm);
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 
         if constexpr (kOut != 0) {
             ptrace = trace_of(P);
-            if (prm.k_gain_steps != nullptr) kgain = gain_trace(P, r, nt);
+            if (prm.k_gain_steps != nullptr) kgain = gain_trace<kBlock>(P, r, nt);
             if (active) {
                 if (prm.x_steps) {
 #pragma unroll
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 #pragma unroll
                         for (int a = 0; a < NX; ++a)
 #pragma unroll
-                            for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, P[tri(a, b)]);
+                            for (int b = 0; b < NX; ++b) st_traj(prm.P_ckpt, base + (long long)(a * NX + b) * N, cpl<kBlock>(a, b) ? P[tri(a, b)] : Real(0));
                     }
                 }
             }
@@ -377,12 +396,12 @@ __global__ void __launch_bounds__(TMA_THREADS, (sizeof(Real) == 4 && !kSummary) 
 #pragma unroll
         for (int a = 0; a < NX; ++a)
 #pragma unroll
-            for (int b = 0; b < NX; ++b) st_traj(prm.P_final, (long long)(a * NX + b) * N + i, P[tri(a, b)]);
+            for (int b = 0; b < NX; ++b) st_traj(prm.P_final, (long long)(a * NX + b) * N + i, cpl<kBlock>(a, b) ? P[tri(a, b)] : Real(0));
     }
     if (kSummary && prm.summary) {
         if (prm.T > 0) {  // of the last step: the posterior P is still in registers
             ptrace = trace_of(P);
-            kgain = gain_trace(P, r, nt);
+            kgain = gain_trace<kBlock>(P, r, nt);
         }
         const double invT = prm.T > 0 ? 1.0 / (double)prm.T : 0.0;
 #pragma unroll

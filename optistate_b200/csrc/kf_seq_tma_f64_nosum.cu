@@ -1,6 +1,6 @@
-// Streamed SEQUENTIAL kernel instantiations: Real = double, kSummary = false (one translation unit per pair, built in parallel).
+// Streamed SEQUENTIAL kernel instantiations: Real = double, kSummary = false, full packed P (one translation unit per variant, built in parallel).
 #include "kf_seq_tma_host.cuh"
 
 namespace okf {
-template int launch_seq_tma<double, false>(const Params<typename Lanes<double>::scalar> &, cudaStream_t);
+template int launch_seq_tma<double, false, false>(const Params<typename Lanes<double>::scalar> &, cudaStream_t);
 }

@@ -41,7 +41,7 @@ bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool kSummary, int kOut, bool kMpc>
+template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock>
 int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
     constexpr int L = Lanes<Real>::n;
     const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
@@ -54,8 +54,8 @@ int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t
     if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw, 12);
     if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw, 12);
     if (!ok) return 1;
-    const size_t smem = TmaSmem<Real>::total(n_lab, kMpc ? TMA_CH_REF : 0, kSummary && sizeof(Real) == 8);
-    auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc>;
+    const size_t smem = TmaSmem<Real>::total(n_lab, kMpc ? TMA_CH_REF : 0, tma_acc_in_smem<Real, kSummary, kBlock>());
+    auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc, kBlock>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     const long long per_block = (long long)TMA_THREADS * L;
     const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
@@ -63,20 +63,30 @@ int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t
     return OPTI_KF_OK;
 }
 
-// per-step outputs and the predict_mpc covariance model are compile-time variants of the kernel (see kf_seq_tma.cuh)
-template <typename Real, bool kSummary>
+// per-step outputs, the predict_mpc covariance model and the decoupled-group form are compile-time variants of the kernel
+// (see kf_seq_tma.cuh); kBlock is chosen by the caller from Params.block and never combines with the predict_mpc model
+template <typename Real, bool kSummary, bool kBlock>
 int launch_seq_tma(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
     const bool rare = p.x_model_steps || p.p_world_steps || p.z_steps || p.P_ckpt;
     const bool estimates = p.x_steps || p.p_trace_steps || p.k_gain_steps || p.nis_steps;
     const int out = rare ? 2 : (estimates ? 1 : 0);
     const bool mpc = p.cov_model == OPTI_KF_COV_MPC;
-    switch (out * 2 + (mpc ? 1 : 0)) {
-        case 0: return launch_seq_tma_k<Real, kSummary, 0, false>(p, stream);
-        case 1: return launch_seq_tma_k<Real, kSummary, 0, true>(p, stream);
-        case 2: return launch_seq_tma_k<Real, kSummary, 1, false>(p, stream);
-        case 3: return launch_seq_tma_k<Real, kSummary, 1, true>(p, stream);
-        case 4: return launch_seq_tma_k<Real, kSummary, 2, false>(p, stream);
-        default: return launch_seq_tma_k<Real, kSummary, 2, true>(p, stream);
+    if constexpr (kBlock) {
+        if (mpc) return OPTI_KF_E_UNSUPPORTED;
+        switch (out) {
+            case 0: return launch_seq_tma_k<Real, kSummary, 0, false, true>(p, stream);
+            case 1: return launch_seq_tma_k<Real, kSummary, 1, false, true>(p, stream);
+            default: return launch_seq_tma_k<Real, kSummary, 2, false, true>(p, stream);
+        }
+    } else {
+        switch (out * 2 + (mpc ? 1 : 0)) {
+            case 0: return launch_seq_tma_k<Real, kSummary, 0, false, false>(p, stream);
+            case 1: return launch_seq_tma_k<Real, kSummary, 0, true, false>(p, stream);
+            case 2: return launch_seq_tma_k<Real, kSummary, 1, false, false>(p, stream);
+            case 3: return launch_seq_tma_k<Real, kSummary, 1, true, false>(p, stream);
+            case 4: return launch_seq_tma_k<Real, kSummary, 2, false, false>(p, stream);
+            default: return launch_seq_tma_k<Real, kSummary, 2, true, false>(p, stream);
+        }
     }
 }
 

@@ -70,6 +70,7 @@ int64_t kf_batch(const std::map<std::string, int64_t> &cfg, const std::map<std::
     d.q_kind = (int32_t)geti(cfg, "q_kind", OPTI_KF_MAT_DIAG);
     d.r_kind = (int32_t)geti(cfg, "r_kind", OPTI_KF_MAT_DIAG);
     d.ckpt_every = geti(cfg, "ckpt_every", 0);
+    d.flags = (int32_t)geti(cfg, "flags", 0);
     d.dt = consts.at("dt");
     d.mass = consts.at("mass");
     d.inertia[0] = consts.at("inertia0");

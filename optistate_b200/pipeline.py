@@ -22,11 +22,13 @@ _STREAM_CH = {"imu": 6, "p": 12, "dp": 12, "contact": 4, "f": 12, "truth": 12, "
 
 class KfHostPipeline:
     def __init__(self, n_traj: int, n_steps: int, n_streams: int, *, dtype: torch.dtype = torch.float64,
-                 labels: Sequence[str] = ("truth", "nominal"), stream_offset: int = 0, n_slots: int = 2, device=None):
+                 labels: Sequence[str] = ("truth", "nominal"), stream_offset: int = 0, n_slots: int = 2, device=None,
+                 structure: str = "auto"):
         nv.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_traj, self.n_steps, self.n_streams, self.dtype = n_traj, n_steps, n_streams, dtype
         self.labels, self.stream_offset, self.n_slots = tuple(labels), int(stream_offset), n_slots
+        self.structure = structure
         esz = 8 if dtype == torch.float64 else 4
         names = ["imu", "p", "dp", "contact", "f", *self.labels]
         self.slots = []
@@ -61,7 +63,8 @@ class KfHostPipeline:
             self.s_k.wait_event(slot["ev_in"])
             kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=dev["Q"], R=dev["R"], n_traj=self.n_traj,
                      dtype=self.dtype, stream_offset=self.stream_offset, truth=dev.get("truth"), nominal=dev.get("nominal"),
-                     outputs=("summary",), out=slot["out"], q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, device=self.device)
+                     outputs=("summary",), out=slot["out"], q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, device=self.device,
+                     structure=self.structure)
             slot["ev_k"].record(self.s_k)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["ev_k"])

@@ -8,10 +8,12 @@ scope) with a no-op class *before* kalman_filter.py binds the name (kalman_filte
 After that `get_odom`, `set_measurements`, `predict`, `update` and `next_state` run unmodified
 on NumPy.  Nothing from the reference is copied into this repository.
 
-The reference tree exists only in the build container, never on the GPU box, so this module is
-used for exactly two things: `oracle/gen_golden.py` (mints tests/golden/*.npz) and the CPU-side
-tests that cross-check the restatements in this directory against the live reference (those
-tests skip when the tree is absent).  Product code must never import it.
+The reference tree exists only in the build container; on the GPU box the same files are found in
+oracle/_ref/ (verbatim copies staged by oracle/make_ref.py at build time, git-ignored).  This module
+is used by `oracle/gen_golden.py` (mints tests/golden/*.npz), by the CPU-side tests that cross-check
+the restatements in this directory against the live reference (they skip when neither tree exists),
+and by bench.py's `cpu_baseline` leg, which times the reference class itself on the box's host cores.
+Product code must never import it.
 """
 from __future__ import annotations
 
@@ -22,7 +24,13 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REF_ROOT = os.environ.get("OPTISTATE_REF", "/root/reference")
+def _default_root() -> str:
+    from . import make_ref
+
+    return make_ref.root() or "/root/reference"
+
+
+REF_ROOT = os.environ.get("OPTISTATE_REF") or _default_root()
 _CASADI_NAMES = ["casadi", "vertcat", "horzcat", "mtimes", "if_else", "cos", "sin", "tan", "transpose", "inv", "skew"]
 
 

@@ -57,7 +57,7 @@ def _desc_class(lib):
                     + [(n, P) for n in ("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "nis_steps")]
                     + [("ckpt_every", I64)]
                     + [(n, P) for n in ("P_ckpt", "x_final", "P_final", "K_final", "summary", "status", "workspace")]
-                    + [("workspace_bytes", ctypes.c_size_t), ("summary_ld", I64), ("n_summary_peers", I32), ("reserved0", I32),
+                    + [("workspace_bytes", ctypes.c_size_t), ("summary_ld", I64), ("n_summary_peers", I32), ("flags", I32),
                        ("summary_peers", P * 7)])
 
     lib.optistate_kf_desc_size.restype = ctypes.c_size_t
@@ -141,7 +141,7 @@ def test_extension_loads_and_refuses_cpu_tensors():
     from optistate_b200 import _native as nv
 
     ext = nv.ext()
-    assert ext.abi_version() == 2 and ext.MAX_PEERS == 7 and ext.launch_count() >= 0
+    assert ext.abi_version() == 3 and ext.MAX_PEERS == 7 and ext.launch_count() >= 0
     cfg = dict(dtype=nv.F64, n_traj=1, n_steps=1, n_streams=1)
     consts = dict(dt=0.01, mass=8.8, inertia0=0.05, inertia1=0.06, inertia2=0.1, gravity=-9.81)
     with pytest.raises(RuntimeError, match="CUDA tensor"):

@@ -100,3 +100,22 @@ def test_live_reference_agrees_with_golden_and_oracle():
     assert np.array_equal(ref["x"], g["x"])
     o = run_c_oracle("edge_dense_noise")
     assert parity.state_err(o["x_steps"][:, :, 0], ref["x"]) < 1e-12
+
+
+def test_reference_goldens_have_exact_zero_cross_group_covariance():
+    """What the decoupled-group kernels rely on (kf_seq_core.cuh, include/optistate_kf.h OPTI_KF_FLAG_*): in the outputs of the
+    UNMODIFIED reference, every covariance entry across the groups {th, w}, {x, vx}, {y, vy}, {z, vz} is an exact floating-point
+    zero whenever P0, Q and R are diagonal and the model is predict() - after 10,000 steps and under the Q_R.pkl noise as
+    well; dense noise, a dense P0 or the predict_mpc model (element-wise exp) fill them."""
+    g = np.array([0, 0, 0, 1, 2, 3, 0, 0, 0, 1, 2, 3])
+    cross = g[:, None] != g[None, :]
+    for name in ["cfg1_default_seed0", "default_seed11_10k", "stress_qrpkl_seed3_10k", "edge_zero_attitude_spin", "edge_yaw_quarter_turn",
+                 "edge_contact_patterns", "edge_large_angles"]:
+        gold = cases.load_golden(name)
+        for key in ("P_ckpt", "P_final"):
+            P = np.asarray(gold[key]).reshape(-1, 12, 12)
+            assert np.abs(P[:, cross]).max() == 0.0, (name, key)
+            assert np.abs(P[:, ~cross]).min() > 0.0, (name, key)
+    for name in ["edge_dense_noise", "edge_nonsymmetric_p0", "next_mpc_cov_seed5"]:
+        P = np.asarray(cases.load_golden(name)["P_final"]).reshape(12, 12)
+        assert np.abs(P[cross]).max() > 0.0, name

@@ -55,10 +55,13 @@ def compare_golden(name, res, tol_x, tol_p, tol_tr):
 
 
 @pytest.mark.parametrize("name", DIAG_CASES)
-@pytest.mark.parametrize("algo", ["sequential", "joint"])
+@pytest.mark.parametrize("algo", ["sequential", "sequential-full", "joint"])
 def test_fp64_matches_reference_golden(name, algo):
-    """north_star: FP64 within 1e-9 relative on states and covariances."""
-    res = run_case(name, algo)
+    """north_star: FP64 within 1e-9 relative on states and covariances.  "sequential" runs the decoupled-group kernels
+    (these cases start from a diagonal P0), "sequential-full" the same recursion on all 78 packed entries."""
+    kw = dict(structure="full") if algo == "sequential-full" else {}
+    algo = algo.split("-")[0]
+    res = run_case(name, algo, **kw)
     assert res.algo == algo
     errs = compare_golden(name, res, parity.FP64_TOL, parity.FP64_TOL, parity.FP64_TOL)
     assert errs["P_corr"] < 1e-7  # entry-scaled covariance error, see tests/parity.py
@@ -438,27 +441,86 @@ def test_custom_model_constants_and_degenerate_sizes(algo):
     assert empty_n.x_final.shape == (12, 0)
 
 
-def test_bench_native_arm_prints_the_contract_line():
-    """bench.py on a small workload: every key of the measurement contract is present and self-consistent."""
-    import json
-    import os
-    import subprocess
-    import sys
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_decoupled_group_kernels_are_bit_identical_to_the_full_recursion(dtype, monkeypatch):
+    """predict()'s F_d couples attitude only with body rate and each position only with its own velocity; with a P0 without
+    cross-group entries those entries of P are exact zeros at every step (in the reference goldens too:
+    tests/test_oracle.py::test_reference_goldens_have_exact_zero_cross_group_covariance), so the kernels that skip them
+    (structure="auto") must return the SAME BITS as the ones that carry all 78 entries (structure="full") - streamed and
+    direct-load kernels, every per-step output, the summary, ragged last block."""
+    from optistate_b200.synth import monte_carlo_noise
 
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--traj-per-gpu", "8192", "--T", "60",
-                          "--streams", "128", "--no-cpu-baseline"], capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stderr[-3000:]
-    d = json.loads(out.stdout.strip().splitlines()[-1])
-    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
-              "config", "e2e", "gpu_launches", "clocks", "roofline"):
-        assert k in d, k
-    assert d["metric"] == "kf_trajectory_steps_per_sec" and d["unit"] == "trajectory-steps/s" and d["n_gpus"] == 1 and d["dtype"] == "f64"
-    assert d["steps"] == 2 and d["warmup"] == 3 and d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
-    assert abs(d["value"] - 8192 * 60 * 2 / (d["ms_per_step"] * 2e-3)) < 1e-6 * d["value"]
-    assert d["gpu_launches"] >= 2 * 2  # measurement pre-pass + filter kernel per step
-    e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 52 * 8192 * 8
-    r = d["roofline"]
-    assert r["bound"] == "fma" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["peak"] > 10
-    assert d["status_nonzero_trajectories"] == 0 and d["clocks"]["sm_mhz"] is not None
+    S, T, N = 128, 200, 300
+    st = make_streams(range(900, 900 + S), T)
+    q, r = monte_carlo_noise(np.arange(N), np.diag(cases.Q_DEFAULT), np.diag(cases.R_DEFAULT))
+    rng = np.random.default_rng(3)
+    x0 = cases.START[:, None] + 0.01 * rng.standard_normal((12, N))
+    p0 = np.abs(rng.standard_normal((12, N))) * 0.01 + 1e-3
+    outs = ("x_steps", "x_model_steps", "p_trace", "k_gain", "nis", "final", "P_ckpt", "summary")
+    base = dict(Q=q, R=r, x0=x0, P0=p0, p0_kind=2, n_traj=N, dtype=dtype, outputs=outs, ckpt_every=50, truth=st["truth"], nominal=0.5 * st["truth"])
+    idx = (np.arange(N) % S).astype(np.int32)
+    variants = [dict(), dict(stream_index=idx), dict(outputs=("summary",)), dict(outputs=("x_final",))]
+    if dtype == torch.float32:
+        variants.append(dict(_packed="0"))  # one FP32 trajectory per thread instead of the packed pair kernel
+    for v in variants:
+        v = dict(v)
+        if "_packed" in v:
+            monkeypatch.setenv("OPTISTATE_KF_PACKED", v.pop("_packed"))
+        kw = dict(base, **v)
+        blk = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
+        full = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], structure="full", **kw)
+        monkeypatch.delenv("OPTISTATE_KF_PACKED", raising=False)
+        assert blk.algo == full.algo == "sequential"
+        for name, t in full.tensors.items():
+            assert torch.equal(blk.tensors[name], t), (name, v, float((blk.tensors[name] - t).abs().max()))
+        assert torch.equal(blk.status, full.status)
+    # the covariance really is block structured ...
+    P = full.P_matrix("P_final") if "P_final" in full.tensors else None
+    full = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], structure="full", **base)
+    g = np.array([0, 0, 0, 1, 2, 3, 0, 0, 0, 1, 2, 3])
+    cross = torch.from_numpy(g[:, None] != g[None, :]).cuda()
+    P = full.P_matrix("P_final")
+    assert float(P[:, cross].abs().max()) == 0.0 and float(P[:, ~cross].abs().min()) > 0.0
+    # ... a dense P0 that has the structure (the P_final of a previous call) is recognised and resumes bit for bit,
+    half = T // 2
+    cut = lambda a, b: {k: np.ascontiguousarray(st[k][a:b]) for k in ("imu", "p", "dp", "contact", "f")}  # noqa: E731
+    one = kf_batch(*cut(0, T).values(), Q=q, R=r, x0=x0, n_traj=N, dtype=dtype, outputs=("final",))
+    a = kf_batch(*cut(0, half).values(), Q=q, R=r, x0=x0, n_traj=N, dtype=dtype, outputs=("final",))
+    b = kf_batch(*cut(half, T).values(), Q=q, R=r, x0=a.x_final, P0=a.P_final, p0_kind=4, n_traj=N, dtype=dtype, outputs=("final",))
+    assert torch.equal(b.x_final, one.x_final) and torch.equal(b.P_final, one.P_final)
+    # ... and a dense symmetric P0 WITH cross-group entries takes the full recursion and matches the oracle
+    if dtype == torch.float64:
+        m = rng.standard_normal((12, 12)) * 0.02
+        p0_dense = m @ m.T + np.diag(np.full(12, 0.01))
+        sub = {k: np.ascontiguousarray(v[:, :, :8]) for k, v in st.items()}
+        ref = c_oracle.run(sub, P0=p0_dense, want=("x_steps", "P_final"))
+        res = kf_batch(sub["imu"], sub["p"], sub["dp"], sub["contact"], sub["f"], P0=p0_dense, outputs=("x_steps", "P_final"))
+        assert res.algo == "sequential"
+        assert parity.rel_err(res.x_steps.cpu().numpy(), ref["x_steps"]) < 1e-9 and parity.rel_err(res.P_final.cpu().numpy(), ref["P_final"]) < 1e-9
+        assert float(res.P_matrix("P_final")[:, cross].abs().max()) > 0.0
+
+
+def test_full_size_config3_shape_fp64_properties():
+    """The bench workload exactly as bench.py times it - kf_seq_tma_kernel<double, summary, no per-step outputs> on 1,048,576
+    trajectories x 1,000 steps over 1,024 shared streams with Monte-Carlo Q / R (BASELINE configs[2] shape, FP64) - checked
+    through size-independent properties and a sample of members against the C oracle at the north-star tolerance."""
+    import bench
+
+    S, T, N = 1024, 1000, 1 << 20
+    st = make_streams(range(S), T)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in st.items()}
+    q, r = bench.mc_noise(0, N, S)
+    q[:, -S:] = q[:, S:2 * S]
+    r[:, -S:] = r[:, S:2 * S]
+    nominal = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], outputs=("x_steps",)).x_steps
+    res = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=q, R=r, n_traj=N, truth=dev["truth"], nominal=nominal,
+                   outputs=("summary",), q_kind=2, r_kind=2)
+    torch.cuda.synchronize()
+    sm = res.summary
+    assert int(res.status.max()) == 0 and bool(torch.isfinite(sm).all())
+    assert float(sm[36:48, :S].abs().max()) == 0.0 and float(sm[36:48, S:].abs().max()) > 0.0
+    assert torch.equal(sm[:, -S:], sm[:, S:2 * S])
+    sample = np.array([0, 5, S - 1, S, S + 17, 123457, N // 2 - 1, N // 2, N - S, N - 1])
+    err = bench.parity_sample(st, q[:, sample], r[:, sample], (sample % S).astype(np.int32), sm[:, sample].cpu().numpy(), nominal.cpu().numpy())
+    print("config-3 shape FP64 sample vs oracle:", err)
+    assert err["max_rel_x"] < 1e-9 and err["max_rel_p"] < 1e-9 and err["max_rel_rmse"] < 1e-9

@@ -1,5 +1,5 @@
 """Developer helper (GPU box): trajectory-steps/s of single bench-shaped launches (1 M trajectories, per-member Q/R).
-usage: python tools/rate.py f64:summary f64:x_final f32:summary f64:x_steps ...   (env CASE_N, CASE_T)"""
+usage: python tools/rate.py f64:summary f64:x_final f32:summary f64:x_steps ...   (env CASE_N, CASE_T, CASE_STRUCTURE=auto|full)"""
 import os
 import sys
 
@@ -21,7 +21,7 @@ for spec in sys.argv[1:]:
     dev = {k: torch.from_numpy(v).to("cuda", dt) for k, v in st.items()}
     n = N if out != "x_steps" else min(N, 1 << 18)
     kw = dict(Q=torch.from_numpy(q64[:, :n].copy()).to("cuda", dt), R=torch.from_numpy(r64[:, :n].copy()).to("cuda", dt),
-              q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, n_traj=n, dtype=dt, outputs=(out,))
+              q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, n_traj=n, dtype=dt, outputs=(out,), structure=os.environ.get("CASE_STRUCTURE", "auto"))
     if out == "mpc":  # predict_mpc covariance model, summary output
         out = "summary"
         kw.update(outputs=("summary",), cov_model="mpc", body_ref=dev["truth"])
