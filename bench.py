@@ -201,7 +201,7 @@ def parity_sample(st, q, r, stream_idx, summary_cols, nominal_x_steps=None):
 
     n = len(stream_idx)
     ref = c_oracle.run(st, n, Q=np.ascontiguousarray(q), R=np.ascontiguousarray(r), stream_index=np.asarray(stream_idx, np.int32),
-                       want=("x_steps", "P_final", "nis_steps", "p_trace_steps", "k_gain_steps"))
+                       noise_per_traj=True, want=("x_steps", "P_final", "nis_steps", "p_trace_steps", "k_gain_steps"))
     x = ref["x_steps"]  # [T, 12, n]
     T = x.shape[0]
     rows = {"x": (slice(0, 12), x[-1]), "p": (slice(12, 24), ref["P_final"][::13]),

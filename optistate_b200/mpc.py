@@ -55,16 +55,19 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
     return forces, status
 
 
-def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=None, R=None, **kw):
+def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=None, R=None, *, dt: float = INITIAL_PARAMS.DT_mpc,
+                             mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None, gravity: float = INITIAL_PARAMS.GRAVITY, **mpc_kw):
     """The reference's closed loop `KF.estimate_state_mpc(imu, p, dp, body_ref, contact)` (kalman_filter.py:176-182) for N
     trajectories over T steps, everything on the device: at every step the force MPC is solved for each trajectory from
     its CURRENT state estimate, then one filter step runs with those forces and the predict_mpc covariance model.
 
     imu [T,6,N], p [T,12,N], dp [T,12,N], contact [T,4,N], body_ref [T,5,12,N] (horizon reference of each step; the
-    filter's transition uses its first column, as the class does).  Returns (x_steps [T,12,N], forces [T,12,N] - the
-    applied stage-0 forces -, mpc_status [T,N], filter status [N]).
+    filter's transition uses its first column, as the class does).  x0, P0, Q, R as in kf_batch (P0 None = Q); dense Q / R or a
+    non-symmetric P0 run the filter step in its joint form, like the class.  dt, mass, inertia, gravity are the model constants
+    of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs) goes to mpc_forces only.
+    Returns (x_steps [T,12,N], forces [T,12,N] - the applied stage-0 forces -, mpc_status [T,N], filter status [N]).
     """
-    from .batch import _as_device, kf_batch
+    from .batch import _as_device, _noise, kf_batch
 
     nv.require_cuda()
     device = torch.device("cuda", torch.cuda.current_device())
@@ -72,26 +75,34 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     T, N = imu.shape[0], imu.shape[2]
     x = _as_device(INITIAL_PARAMS.STARTING_STATE.reshape(12) if x0 is None else x0, torch.float64, device)
     x = x.reshape(12, 1).repeat(1, N) if x.numel() == 12 else x.reshape(12, N).clone()
-    Pm = None if P0 is None else _as_device(P0, torch.float64, device)
     xs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
     fs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
     mst = torch.empty((T, N), dtype=torch.int32, device=device)
     fst = torch.zeros(N, dtype=torch.int32, device=device)
-    # everything that would make a step synchronise with the host is settled once: diagonal noise as device vectors, the
-    # bound on the legs out of swing over all steps, and the symmetry of P (the packed-symmetric filter keeps it exactly)
-    q_d = torch.diagonal(_as_device(INITIAL_PARAMS.Q if Q is None else Q, torch.float64, device).reshape(12, 12)).contiguous() \
-        if Q is None or np.shape(Q) == (12, 12) else _as_device(Q, torch.float64, device)
-    r_d = torch.diagonal(_as_device(INITIAL_PARAMS.R if R is None else R, torch.float64, device).reshape(10, 10)).contiguous() \
-        if R is None or np.shape(R) == (10, 10) else _as_device(R, torch.float64, device)
-    if "max_free_legs" not in kw:
-        kw["max_free_legs"] = max(1, int((contact != 0).sum(dim=1).max())) if T * N > 0 else 4
+    # everything that would make a step synchronise with the host is settled once, before the loop: the classification of the
+    # noise arguments (a dense matrix that is exactly diagonal becomes a diagonal), the symmetry of the initial P, the bound
+    # on the legs out of swing over all steps
+    q_t, q_kind = _noise(INITIAL_PARAMS.Q if Q is None else Q, 12, N, "Q", torch.float64, device)
+    r_t, r_kind = _noise(INITIAL_PARAMS.R if R is None else R, 10, N, "R", torch.float64, device)
+    diag_noise = q_kind in (nv.MAT_DIAG, nv.MAT_DIAG_PER) and r_kind in (nv.MAT_DIAG, nv.MAT_DIAG_PER)
+    Pm, p_kind, p_sym = None, None, True
+    if P0 is not None:
+        Pm, p_kind = _noise(P0, 12, N, "P0", torch.float64, device)
+        if p_kind in (nv.MAT_DENSE, nv.MAT_DENSE_PER):
+            m = Pm.reshape(12, 12, -1)
+            p_sym = bool(torch.equal(m, m.transpose(0, 1)))
+    algo = "sequential" if (diag_noise and p_sym) else "joint"  # the packed-symmetric form needs diagonal noise and a symmetric P
+    model = dict(dt=dt, mass=mass, inertia=inertia, gravity=gravity)
+    if "max_free_legs" not in mpc_kw:
+        mpc_kw["max_free_legs"] = max(1, int((contact != 0).sum(dim=1).max())) if T * N > 0 else 4
     for t in range(T):
-        forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **kw)
+        forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **model, **mpc_kw)
         fs[t], mst[t] = forces[0], st
-        res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=q_d, R=r_d, n_traj=N,
-                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"), algo="sequential",
-                       p0_kind=None if Pm is None else nv.MAT_DENSE_PER, p0_is_symmetric=True)
-        x, Pm = res.x_final, res.P_final
+        res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=q_t, R=r_t, n_traj=N,
+                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"), algo=algo, q_kind=q_kind, r_kind=r_kind,
+                       p0_kind=p_kind, p0_is_symmetric=p_sym, **model)
+        # the fed-back covariance: dense per trajectory; symmetric by construction on the packed-symmetric path
+        x, Pm, p_kind = res.x_final, res.P_final, nv.MAT_DENSE_PER
         xs[t] = x
         fst |= res.status
     return xs, fs, mst, fst

@@ -59,12 +59,13 @@ def _ptr(a, typ=_DP):
 
 
 def run(streams, n_traj=None, *, Q=None, R=None, x0=None, P0=None, stream_index=None, cov_model=0,
-        ckpt_every=0, n_threads=0, want=("x_steps", "p_trace_steps", "k_gain_steps", "x_final", "P_final"),
+        ckpt_every=0, n_threads=0, noise_per_traj=None, want=("x_steps", "p_trace_steps", "k_gain_steps", "x_final", "P_final"),
         dt=0.01, mass=8.8, inertia=(55303643.08 / 10**9, 60119440.34 / 10**9, 105304340.05 / 10**9), gravity=-9.81):
     """Filters n_traj trajectories over base streams laid out [T, C, S] (float64).
 
     Q: [12,12] shared dense or [12,N] per-trajectory diagonal;  R: [10,10] or [10,N];
     x0: [12] or [12,N];  P0: None (= Q), [12,12] or [144,N].  Returns dict of the arrays named in `want`.
+    noise_per_traj: True / False settles how a [12,12] Q (N = 12) or [10,10] R (N = 10) is read; None = shared dense.
     """
     from .kf_numpy import Q_DEFAULT, R_DEFAULT, START
 
@@ -79,8 +80,8 @@ def run(streams, n_traj=None, *, Q=None, R=None, x0=None, P0=None, stream_index=
     a.inertia = (C.c_double * 3)(*inertia)
     Q = f64(np.diag(Q_DEFAULT) if Q is None else Q)
     R = f64(np.diag(R_DEFAULT) if R is None else R)
-    a.q_kind = 0 if Q.shape == (12, 12) and not (N == 12 and streams.get("_q_diag")) else 1
-    a.r_kind = 0 if R.shape == (10, 10) and not (N == 10 and streams.get("_r_diag")) else 1
+    a.q_kind = 0 if Q.shape == (12, 12) and not (N == 12 and noise_per_traj) else 1
+    a.r_kind = 0 if R.shape == (10, 10) and not (N == 10 and noise_per_traj) else 1
     if a.q_kind == 1:
         assert Q.shape == (12, N), Q.shape
     if a.r_kind == 1:

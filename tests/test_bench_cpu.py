@@ -32,7 +32,7 @@ def test_executed_flops_and_traffic_come_from_the_committed_ncu_summaries():
 
 def test_current_profiles_describe_the_kernels_that_are_built():
     """Every r2 hot-loop summary must name an instantiation that exists in the built library, and its executed FP count must
-    not exceed the static count of that kernel's time loop (tools/sass_loop.py): an edit of the kernel that is not followed by
+    not exceed the static count of that kernel's time loop (tools/sass_loop.py; the static loop also holds the rare slow paths): an edit of the kernel that is not followed by
     a new capture shows up here."""
     import glob
 
@@ -51,7 +51,7 @@ def test_current_profiles_describe_the_kernels_that_are_built():
         assert len(hist) == 1, (mangled, list(hist))
         h, _ = next(iter(hist.values()))
         _, n_static = sass_loop.flops(h)
-        assert 0.6 * n_static <= prof["fp_instructions_per_thread_step"] <= n_static, (f, n_static, prof["fp_instructions_per_thread_step"])
+        assert 0.5 * n_static <= prof["fp_instructions_per_thread_step"] <= n_static, (f, n_static, prof["fp_instructions_per_thread_step"])
 
 
 def test_job_shapes_and_noise_law():
@@ -92,6 +92,25 @@ def test_parity_sample_is_zero_against_itself_and_sees_a_wrong_member():
     assert e["n"] == 4 and max(v for k, v in e.items() if k.startswith("max_rel_")) == 0.0
     sm[5, 2] *= 1.0 + 1e-6
     assert bench.parity_sample(st, q, r, idx, sm, nominal)["max_rel_x"] > 1e-7
+
+
+def test_parity_sample_with_ten_and_twelve_members_reads_the_noise_per_trajectory():
+    """A sample of exactly 10 (12) members hands the oracle a [10, 10] R ([12, 12] Q): it must still be read as per-trajectory
+    diagonals, not as one shared dense matrix (this made the full-size FP64 test fail on its first GPU run)."""
+    from oracle import c_oracle
+    from optistate_b200.synth import make_streams
+
+    st = make_streams(range(4), 40)
+    for n in (10, 12):
+        idx = (np.arange(n) % 4).astype(np.int32)
+        q, r = bench.mc_noise(4, n, 4)
+        batch = c_oracle.run(st, n, Q=q, R=r, stream_index=idx, noise_per_traj=True, want=("x_final",))["x_final"]
+        for k in range(n):
+            one = c_oracle.run(st, 1, Q=q[:, [k]], R=r[:, [k]], stream_index=idx[k:k + 1], want=("x_final",))["x_final"]
+            assert np.array_equal(one[:, 0], batch[:, k]), (n, k)
+        sm = np.zeros((52, n))
+        sm[0:12] = batch
+        assert bench.parity_sample(st, q, r, idx, sm)["max_rel_x"] == 0.0
 
 
 def test_clock_sampler_survives_a_box_without_gpu_or_nvml():
