@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define OPTISTATE_KF_ABI_VERSION 3
+#define OPTISTATE_KF_ABI_VERSION 4
 
 #define OPTI_KF_NX 12 /* states  [thx thy thz | x y z | wx wy wz | vx vy vz]   kalman_filter.py:9  */
 #define OPTI_KF_NZ 10 /* measurements [th_imu(3) z_odom w_imu(3) v_odom(3)]    kalman_filter.py:11 */
@@ -237,7 +237,8 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *desc, void *cuda_strea
 enum { OPTI_KF_MPC_ST_IPM_LIMIT = 1,  /* interior-point phase stopped on its iteration cap or a pivot breakdown       */
        OPTI_KF_MPC_ST_UNPOLISHED = 2, /* active-set polish did not settle: the forces are the interior-point iterate
                                          (~1e-6 relative) instead of the exact vertex solution                         */
-       OPTI_KF_MPC_ST_TOO_MANY_LEGS = 4 /* more legs out of swing than max_free_legs promised: forces are NaN          */ };
+       OPTI_KF_MPC_ST_TOO_MANY_LEGS = 4, /* more legs out of swing than max_free_legs promised: forces are NaN         */
+       OPTI_KF_MPC_ST_WARM = 8         /* informational: the warm-start active set was verified, no interior-point phase */ };
 typedef struct OptiKfMpcDesc {
     uint32_t struct_size, abi_version;
     int32_t dtype;                 /* OPTI_KF_F64 */
@@ -250,6 +251,17 @@ typedef struct OptiKfMpcDesc {
     const void *contact;           /* [4][N] 0 / 1 flags stored as dtype, held over the horizon (kalman_filter.py:145-146) */
     void *forces;                  /* [5][12][N] optimal forces; stage 0 is what predict_mpc applies (kalman_filter.py:161) */
     uint32_t *status;              /* [N] optional: OPTI_KF_MPC_ST_* | interior-point iterations << 8                  */
+    /* Optional warm start for closed loops (estimate_state_mpc solves a near-identical QP every step), in / out, both or
+     * neither: the active set (one word per stage: bit 5 leg + row, bits 24..27 legs out of swing, bit 31 valid; zeroed
+     * memory = no warm start) and the multipliers of its rows.  A set that verifies (primal and dual feasibility of the
+     * equality-constrained solve, the same test that ends the cold path) skips the interior-point phase; one that does
+     * not, or a changed contact pattern, falls back to it.  Used for max_free_legs <= 2, ignored otherwise.            */
+    uint32_t *warm_set;            /* [5][N]                                                                           */
+    void *warm_mult;               /* [5][4][5][N] doubles                                                              */
+    int32_t warm_rounds;           /* active-set correction rounds a warm start may take before the interior point runs
+                                      (0 = default)                                                                    */
+    int32_t solver;                /* max_free_legs <= 2: 0 = dual active set, interior point for what it gives up on (default);
+                                      1 = interior point only.  A warm start implies 1.                                */
     double dt, mass, inertia[3], gravity;
     double mu, fz_max;             /* 0.6, 150 (force_controller.py:149-151)                                          */
     double w_state[12], w_force;   /* diag Q = P (kalman_filter.py:64,70) and the R value (:66)                        */

@@ -480,12 +480,17 @@ int optistate_kf_mpc_forces(const OptiKfMpcDesc *d, void *cuda_stream) {
         if (!(d->w_state[k] >= 0)) return OPTI_KF_E_SHAPE;
     if (d->n_problems == 0) return OPTI_KF_OK;
     if (!d->x || !d->body_ref || !d->p || !d->contact || !d->forces) return OPTI_KF_E_NULL;
+    if ((d->warm_set == nullptr) != (d->warm_mult == nullptr)) return OPTI_KF_E_NULL;
     okf::MpcParams p;
     std::memset(&p, 0, sizeof p);
     p.N = d->n_problems;
     p.max_legs = d->max_free_legs == 0 ? 4 : d->max_free_legs;
     p.x = (const double *)d->x; p.body_ref = (const double *)d->body_ref; p.p = (const double *)d->p;
     p.contact = (const double *)d->contact; p.forces = (double *)d->forces; p.status = d->status;
+    p.warm_set = d->warm_set; p.warm_mult = (double *)d->warm_mult;
+    p.warm_rounds = d->warm_rounds > 0 ? d->warm_rounds : 0;
+    if (d->solver != 0 && d->solver != 1) return OPTI_KF_E_SHAPE;
+    p.solver = d->solver;
     p.dt = d->dt; p.inv_mass = 1.0 / d->mass; p.gravity = d->gravity; p.mu = d->mu; p.fz_max = d->fz_max; p.w_force = d->w_force;
     for (int k = 0; k < 3; ++k) p.inv_inertia[k] = 1.0 / d->inertia[k];
     for (int k = 0; k < 12; ++k) p.w_state[k] = d->w_state[k];

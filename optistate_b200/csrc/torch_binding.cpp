@@ -351,6 +351,18 @@ int kf_mpc_forces(int64_t n, int64_t max_free_legs, const std::map<std::string, 
         TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == n, "optistate_b200: bad 'status'");
         d.status = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
     }
+    auto iw = tensors.find("warm_set");
+    if (iw != tensors.end()) {
+        const at::Tensor &t = iw->second;
+        TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == OPTI_KF_MPC_HORIZON * n,
+                    "optistate_b200: bad 'warm_set'");
+        d.warm_set = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+        d.warm_mult = const_cast<void *>(ck.get(tensors, "warm_mult", OPTI_KF_MPC_HORIZON * 4 * 5 * n, true));
+        auto wr = consts.find("warm_rounds");
+        d.warm_rounds = wr == consts.end() ? 0 : (int32_t)wr->second;
+    }
+    auto sv = consts.find("solver");
+    d.solver = sv == consts.end() ? 0 : (int32_t)sv->second;
     d.dt = consts.at("dt"); d.mass = consts.at("mass"); d.gravity = consts.at("gravity");
     d.inertia[0] = consts.at("inertia0"); d.inertia[1] = consts.at("inertia1"); d.inertia[2] = consts.at("inertia2");
     d.mu = consts.at("mu"); d.fz_max = consts.at("fz_max"); d.w_force = consts.at("w_force");

@@ -18,7 +18,7 @@ W_STATE = (10.0, 10.0, 10.0, 100.0, 100.0, 100.0, 1.0, 1.0, 5.0, 1.0, 1.0, 1.0)
 W_FORCE = 1e-6
 MU = 0.6
 FZ_MAX = 150.0
-ST_IPM_LIMIT, ST_UNPOLISHED, ST_TOO_MANY_LEGS = 1, 2, 4
+ST_IPM_LIMIT, ST_UNPOLISHED, ST_TOO_MANY_LEGS, ST_WARM = 1, 2, 4, 8
 
 
 def _dev64(a, device):
@@ -28,13 +28,18 @@ def _dev64(a, device):
 
 def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
                gravity: float = INITIAL_PARAMS.GRAVITY, mu: float = MU, fz_max: float = FZ_MAX, w_state=W_STATE, w_force: float = W_FORCE,
-               max_free_legs=None, device=None):
+               max_free_legs=None, device=None, warm=None, solver: str = "auto"):
     """Solves N force MPC problems.
 
     x [12, N] current states; body_ref [5, 12, N] reference states of the horizon; p [12, N] body-frame feet;
     contact [4, N] (0 swing, 1 stance).  max_free_legs: bound on the legs out of swing in any problem (None = taken from
-    `contact`, which costs one small reduction and a host sync; it sizes the kernel's shared memory).  Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]:
-    ST_* bits | interior-point iterations << 8).
+    `contact`, which costs one small reduction and a host sync; it sizes the kernel's shared memory).
+    solver: "auto" - for at most two legs out of swing the dual active-set kernel (csrc/kf_mpc_gi.cuh), with the interior-point
+    kernel behind it for problems it gives up on; "interior_point" - the interior-point kernel only (what three and four legs out
+    of swing always get).
+    warm: a `WarmStart` (in / out; an interior-point feature, implies that solver) carrying the active set and multipliers from one solve to the next one of the same
+    problems (closed loops); a set that no longer verifies falls back to the cold path inside the kernel.
+    Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]: ST_* bits | interior-point iterations << 8).
     """
     nv.require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -48,11 +53,34 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
     inertia = np.diag(INITIAL_PARAMS.INERTIA_ROT) if inertia is None else np.asarray(inertia, float).reshape(3)
     consts = dict(dt=float(dt), mass=float(mass), inertia0=float(inertia[0]), inertia1=float(inertia[1]), inertia2=float(inertia[2]),
                   gravity=float(gravity), mu=float(mu), fz_max=float(fz_max), w_force=float(w_force))
+    if solver not in ("auto", "interior_point"):
+        raise ValueError("solver must be 'auto' or 'interior_point'")
+    consts["solver"] = 1.0 if solver == "interior_point" else 0.0
+    tensors = dict(x=x_t, body_ref=b_t, p=p_t, contact=c_t, forces=forces, status=status)
+    if warm is not None:
+        if warm.n != n or warm.active.device != device:
+            raise ValueError("warm start was set up for another batch size or device")
+        tensors.update(warm_set=warm.active, warm_mult=warm.multipliers)
+        consts["warm_rounds"] = float(warm.rounds)
     with torch.cuda.device(device):
-        nv.check(int(nv.ext().kf_mpc_forces(n, int(max_free_legs), consts, [float(w) for w in w_state],
-                                            dict(x=x_t, body_ref=b_t, p=p_t, contact=c_t, forces=forces, status=status))),
-                 "optistate_kf_mpc_forces")
+        nv.check(int(nv.ext().kf_mpc_forces(n, int(max_free_legs), consts, [float(w) for w in w_state], tensors)), "optistate_kf_mpc_forces")
     return forces, status
+
+
+class WarmStart:
+    """Active set and multipliers carried between consecutive solves of the same N problems (include/optistate_kf.h,
+    OptiKfMpcDesc.warm_set / warm_mult).  Starts empty: the first solve is a cold one."""
+
+    def __init__(self, n: int, device=None, rounds: int = 0):
+        nv.require_cuda()
+        self.rounds = int(rounds)  # active-set correction rounds before the interior point takes over (0 = the kernel's default)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = int(n)
+        self.active = torch.zeros((HORIZON, self.n), dtype=torch.int32, device=device)
+        self.multipliers = torch.zeros((HORIZON * 4 * 5, self.n), dtype=torch.float64, device=device)
+
+    def reset(self):
+        self.active.zero_()
 
 
 def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=None, R=None, *, dt: float = INITIAL_PARAMS.DT_mpc,
@@ -64,7 +92,7 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     imu [T,6,N], p [T,12,N], dp [T,12,N], contact [T,4,N], body_ref [T,5,12,N] (horizon reference of each step; the
     filter's transition uses its first column, as the class does).  x0, P0, Q, R as in kf_batch (P0 None = Q); dense Q / R or a
     non-symmetric P0 run the filter step in its joint form, like the class.  dt, mass, inertia, gravity are the model constants
-    of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs) goes to mpc_forces only.
+    of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs, solver, warm) goes to mpc_forces only.
     Returns (x_steps [T,12,N], forces [T,12,N] - the applied stage-0 forces -, mpc_status [T,N], filter status [N]).
     """
     from .batch import _as_device, _noise, kf_batch

@@ -18,12 +18,18 @@ rep = max(1, N // min(N, 1024))
 st = {k: v.repeat(1, 1, rep) for k, v in st.items()}
 ref = torch.zeros((T, 5, 12, st["imu"].shape[2]), dtype=torch.float64, device="cuda")
 ref[:, :, 5] = 0.28
+from optistate_b200.mpc import WarmStart  # noqa: E402
+
+rounds = int(os.environ.get("WARM_ROUNDS", "0"))
 for _ in range(2):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref)
+    kw = {} if rounds <= 0 else {"warm": WarmStart(st["imu"].shape[2], rounds=rounds)}  # default: the dual active-set kernel, cold
+    xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref, **kw)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 n = xs.shape[2]
+it = (mst >> 8).double()
+print("per step: warm accepted", [round(float((mst[t] & 8).ne(0).double().mean()), 2) for t in range(min(T, 12))], "ipm iterations", [round(float(it[t].mean()), 1) for t in range(min(T, 12))])
 print(f"{n} trajectories x {T} steps: {n * T / dt:.3e} trajectory-steps/s ({dt / T * 1e3:.2f} ms per step); unpolished {int((mst & 2).ne(0).sum())}, "
       f"filter status {int(fst.max())}")
