@@ -10,8 +10,8 @@ namespace okf {
 int launch_mpc(const MpcParams &p, cudaStream_t stream) {
     if (p.max_legs <= MPCR_MAX_LEGS) {  // a trot or less: one warp per problem
         // dual active set first (kf_mpc_gi.cuh); the interior point (kf_mpc_rows.cuh) solves what it flags, or everything when
-        // the caller asks for it, passes a warm start (an interior-point feature) or gives no status array to carry the flags
-        const bool gi = p.solver == 0 && p.status != nullptr && p.warm_set == nullptr;
+        // the caller asks for it or gives no status array to carry the flags.  Both take a warm start
+        const bool gi = p.solver == 0 && p.status != nullptr;
         MpcParams q = p;
         if (gi) {
             const size_t smem = mpcg_smem_bytes();

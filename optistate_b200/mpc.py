@@ -37,7 +37,7 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
     solver: "auto" - for at most two legs out of swing the dual active-set kernel (csrc/kf_mpc_gi.cuh), with the interior-point
     kernel behind it for problems it gives up on; "interior_point" - the interior-point kernel only (what three and four legs out
     of swing always get).
-    warm: a `WarmStart` (in / out; an interior-point feature, implies that solver) carrying the active set and multipliers from one solve to the next one of the same
+    warm: a `WarmStart` (in / out) carrying the active set and multipliers from one solve to the next one of the same
     problems (closed loops); a set that no longer verifies falls back to the cold path inside the kernel.
     Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]: ST_* bits | interior-point iterations << 8).
     """
@@ -123,6 +123,8 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     model = dict(dt=dt, mass=mass, inertia=inertia, gravity=gravity)
     if "max_free_legs" not in mpc_kw:
         mpc_kw["max_free_legs"] = max(1, int((contact != 0).sum(dim=1).max())) if T * N > 0 else 4
+    if "warm" not in mpc_kw:  # consecutive QPs of a trajectory differ by one filter step: the working set carries over
+        mpc_kw["warm"] = WarmStart(N, device)
     for t in range(T):
         forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **model, **mpc_kw)
         fs[t], mst[t] = forces[0], st

@@ -143,18 +143,19 @@ def test_warm_start_is_verified_and_falls_back():
     n = 512
     x, ref, p, c = mpc_cases.batch(n, seed=3)
     c[:] = np.where((np.arange(n) % 2 == 0)[None, :], np.array([1.0, 0, 0, 1])[:, None], np.array([0, 1.0, 1, 0])[:, None])
-    warm = WarmStart(n)                                 # (a warm start selects the interior-point kernel, kf_mpc_rows.cuh)
-    cold, st0 = mpc_forces(x, ref, p, c, warm=warm)
+    ip = dict(solver="interior_point")                  # kf_mpc_rows.cuh: the warm set skips the interior-point phase when it verifies
+    warm = WarmStart(n)
+    cold, st0 = mpc_forces(x, ref, p, c, warm=warm, **ip)
     assert not (st0 & (7 | ST_WARM)).any() and int((st0 >> 8).min()) > 0            # interior point everywhere
-    again, st1 = mpc_forces(x, ref, p, c, warm=warm)
+    again, st1 = mpc_forces(x, ref, p, c, warm=warm, **ip)
     assert (st1 & ST_WARM).all() and not (st1 & 7).any() and int((st1 >> 8).max()) == 0
     assert float((again - cold).abs().max()) < 1e-8 * float(cold.abs().max())
     # the next step of a closed loop: states and references move a little
     rng = np.random.default_rng(9)
     x2 = x + 2e-3 * rng.standard_normal(x.shape)
     ref2 = ref + 1e-3 * rng.standard_normal(ref.shape)
-    near, st2 = mpc_forces(x2, ref2, p, c, warm=warm)
-    plain, st2c = mpc_forces(x2, ref2, p, c)
+    near, st2 = mpc_forces(x2, ref2, p, c, warm=warm, **ip)
+    plain, st2c = mpc_forces(x2, ref2, p, c, **ip)
     assert not (st2 & 7).any() and not (st2c & 7).any()
     assert float((st2 & ST_WARM).ne(0).double().mean()) > 0.5, float((st2 & ST_WARM).ne(0).double().mean())
     assert float((near - plain).abs().max()) < 1e-8 * float(plain.abs().max())
@@ -167,6 +168,51 @@ def test_warm_start_is_verified_and_falls_back():
         assert np.abs(u - want).max() < 1e-8 * max(1.0, np.abs(want).max()), k
     # the gait switches legs: the stored sets belong to other legs
     c2 = 1.0 - c
-    sw, st3 = mpc_forces(x2, ref2, p, c2, warm=warm)
-    sw_cold, _ = mpc_forces(x2, ref2, p, c2)
+    sw, st3 = mpc_forces(x2, ref2, p, c2, warm=warm, **ip)
+    sw_cold, _ = mpc_forces(x2, ref2, p, c2, **ip)
     assert not (st3 & (7 | ST_WARM)).any() and float((sw - sw_cold).abs().max()) < 1e-8 * float(sw_cold.abs().max())
+
+
+def test_dual_active_set_warm_start_and_solver_agreement():
+    """The default solver for a trot (kf_mpc_gi.cuh) against the interior-point kernel on the same problems, and its warm start: the
+    working set of one solve, entered by bordering, starts the next one - same minimiser, fewer iterations, also when the set has
+    to change or belongs to other legs."""
+    from optistate_b200.mpc import ST_WARM, WarmStart
+
+    n = 1024
+    x, ref, p, c = mpc_cases.batch(n, seed=11)
+    c[:] = np.where((np.arange(n) % 2 == 0)[None, :], np.array([1.0, 0, 0, 1])[:, None], np.array([0, 1.0, 1, 0])[:, None])
+    c[:, ::17] = np.array([0.0, 1.0, 0.0, 0.0])[:, None]          # a few problems with a single stance leg
+    gi, st = mpc_forces(x, ref, p, c)
+    ipm, st_ip = mpc_forces(x, ref, p, c, solver="interior_point")
+    scale = float(ipm.abs().max())
+    assert not (st & 7).any() and not (st_ip & 7).any()
+    assert float((gi - ipm).abs().max()) < 1e-8 * scale
+    warm = WarmStart(n)
+    first, s0 = mpc_forces(x, ref, p, c, warm=warm)
+    assert torch.equal(first, gi) and not (s0 & ST_WARM).any()
+    again, s1 = mpc_forces(x, ref, p, c, warm=warm)               # same problems: the set is the answer, no constraint enters or leaves
+    constrained = (warm.active[0] & 0xFFFFF) != 0
+    assert float((again - gi).abs().max()) < 1e-9 * scale and bool(((s1 & ST_WARM) != 0)[constrained].all())
+    assert int((s1 >> 8)[constrained].max()) == 0
+    rng = np.random.default_rng(5)
+    x2 = x + 2e-3 * rng.standard_normal(x.shape)
+    ref2 = ref + 1e-3 * rng.standard_normal(ref.shape)
+    near, s2 = mpc_forces(x2, ref2, p, c, warm=warm)
+    plain, s2c = mpc_forces(x2, ref2, p, c)
+    assert not (s2 & 7).any() and float((near - plain).abs().max()) < 1e-8 * scale
+    assert float((s2 >> 8).double().mean()) < 0.5 * float((s2c >> 8).double().mean())   # far fewer constraint changes than from scratch
+    c2 = 1.0 - c
+    c2[:, ::17] = np.array([0.0, 0.0, 1.0, 0.0])[:, None]
+    sw, s3 = mpc_forces(x2, ref2, p, c2, warm=warm)
+    sw_cold, _ = mpc_forces(x2, ref2, p, c2)
+    assert not (s3 & (7 | ST_WARM)).any() and torch.equal(sw, sw_cold)
+    F = near.cpu().numpy()
+    for k in list(range(0, n, 61)) + [0, 17, 34]:
+        H, g, _ = mpc.build_qp(x2[:, k], ref2[:, :, k].T, p[:, k])
+        A, b, pinned = mpc.constraints(c[:, k])
+        want = mpc.solve_ldp(H, g, A, b, pinned)
+        u = F[:, :, k].reshape(-1)
+        assert np.abs(u - want).max() < 1e-8 * max(1.0, np.abs(want).max()), k
+        viol, stat = mpc.kkt_certificate(u, H, g, A, b, pinned)
+        assert viol < 1e-7 and stat < 1e-8, (k, viol, stat)
