@@ -2,12 +2,16 @@
 // P and x in registers, sequential scalar updates) with the per-step inputs delivered by the TMA engine.
 //
 //   * 32 consecutive trajectories (one warp) read 32 consecutive base streams, so the inputs of one step are
-//     [C] x 32 tiles of the [T*C][S] arrays.  Each warp runs its OWN input pipeline: one elected lane issues a
-//     2-D tensor-map copy (cp.async.bulk.tensor, SASS UTMALDG) per array - p, f, z, label streams - that lands the
-//     tile in the warp's slice of shared memory and completes on a warp-private mbarrier (complete_tx).  No
-//     per-thread address arithmetic, no LDG in the recursion, no registers tied up by loads in flight, and no
-//     block-wide barrier: warps never wait for each other.
-//   * Three channel groups, each single-buffered and refilled for step t+1 the moment the warp has consumed
+//     [C] x 32 tiles of the [T*C][S] arrays, delivered by 2-D tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG)
+//     per array - p, f, z, label streams - that complete on an mbarrier (complete_tx).  No per-thread address
+//     arithmetic, no LDG in the recursion, no registers tied up by loads in flight, no block-wide barrier.
+//   * The FOUR WARPS OF A BLOCK SHARE ONE TILE: they filter four different members (trajectory i, i + S, i + 2 S, i + 3 S)
+//     of the same 32 streams, so one copy feeds all of them and the block needs 15 KB of input tiles instead of 59 KB.
+//     That is what decides occupancy: with a tile per warp the decoupled-group kernels (168 registers, three blocks per
+//     SM by registers) were held to two blocks by 108 KB of shared memory; with the shared tile three blocks fit
+//     (ncu: launch__occupancy_limit_shared_mem).  The warp that is LAST to finish reading a group (a shared-memory
+//     counter) issues the refill, so nobody waits on a designated producer.
+//   * Three channel groups, each single-buffered and refilled for step t+1 the moment the block has consumed
 //     step t's copy, so the copy has most of a filter step (several microseconds) to land:
 //         G0 = p[12] f[12]      read at the top of the step (mean model)        -> refilled right away
 //              (+ the 3 reference body angles of the predict_mpc covariance model in the kMpc instantiations)
@@ -76,19 +80,20 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, 
 
 template <typename Real>
 struct TmaSmem {
-    // dynamic shared memory: [mbarriers 128 B][per warp: G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] x 4 warps
-    //                        [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
+    // dynamic shared memory: [mbarriers + counters 128 B][G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] (one tile
+    //                        set per block)  [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
     static __host__ __device__ constexpr size_t warp_rows(int n_lab, int ref_rows) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab + ref_rows; }
     static __host__ __device__ constexpr size_t warp_bytes(int n_lab, int ref_rows) { return warp_rows(n_lab, ref_rows) * 32 * sizeof(Real); }
     static __host__ __device__ constexpr size_t off_in() { return 128; }
-    static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + TMA_WARPS * warp_bytes(n_lab, ref_rows); }
+    static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + warp_bytes(n_lab, ref_rows); }
     static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
     static __host__ __device__ constexpr size_t total(int n_lab, int ref_rows, bool acc_in_smem) {
         return off_acc(n_lab, ref_rows) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * 8 : 0);
     }
 };
 
-// One elected lane per warp: arm the group's mbarrier with the byte count, then issue the tile copies of step t.
+// One elected thread (`lane` == 0 of the warp that is entitled to refill): arm the group's mbarrier with the byte count, then
+// issue the tile copies of step t.
 template <bool kMpc, typename Real>
 __device__ __forceinline__ void issue_g0(const TmaMaps &m, long long t, int s_warp, Real *g0w, Real *refw, uint64_t *bar, int lane) {
     if (lane == 0) {
@@ -149,49 +154,61 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
     constexpr int nt = TMA_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = prm.N, S = prm.S;
-    // Trajectory block b reads stream tile b % n_tiles.  Launch order is permuted so that consecutive (= co-resident)
-    // blocks share ONE stream tile: its whole time series (tens of MB) then stays L2-resident no matter how far the
-    // resident blocks drift apart in time, instead of every block streaming its tile from HBM again (measured: 375 GB
-    // -> ~1 GB of DRAM reads per launch on the 1 M x 1 k sweep).
-    long long blk = blockIdx.x;
-    {
-        const long long per_block = (long long)nt * L;
-        const long long n_tiles = (S % per_block == 0) ? S / per_block : 1;
-        if (n_tiles > 1) {
-            const long long nb = gridDim.x, base = nb / n_tiles, rem = nb % n_tiles, q = blockIdx.x;
-            long long k, j;
-            if (q < rem * (base + 1)) { k = q / (base + 1); j = q % (base + 1); }
-            else { const long long q2 = q - rem * (base + 1); k = rem + q2 / base; j = q2 % base; }
-            blk = j * n_tiles + k;
-        }
-    }
-    const long long i0 = blk * nt * L;  // first trajectory of the block
-    const long long i = i0 + (long long)tid * L;           // first trajectory of this thread
-    const bool active = i < N;                             // N % L == 0 is guaranteed by the host
+    // Block (tile k, group j) filters members 4 j .. 4 j + 3 of the 32 L streams of tile k: warp w owns trajectories
+    // (4 j + w) S + 32 L k + L lane (+ 0 .. L-1), which all read stream tile k (shifted by the stream offset).  Blocks of one
+    // tile are launched next to each other, so the tile's whole time series (tens of MB) stays L2-resident however far the
+    // resident blocks drift apart in time (measured in round 1: 375 GB -> ~1 GB of DRAM reads per launch on the 1 M x 1 k sweep).
+    constexpr int TW = 32 * L;                                     // streams of a tile = trajectories of a warp
+    const long long n_pass = (N + S - 1) / S;                      // members per stream (the last pass may be ragged)
+    const long long groups = (n_pass + TMA_WARPS - 1) / TMA_WARPS;  // blocks per tile
+    const long long tile_k = blockIdx.x / groups, grp_j = blockIdx.x % groups;
+    const long long m_pass = grp_j * TMA_WARPS + warp;
+    const bool warp_active = m_pass < n_pass;
+    const int n_active = (int)(n_pass - grp_j * TMA_WARPS < TMA_WARPS ? n_pass - grp_j * TMA_WARPS : TMA_WARPS);  // warps of this block with work
+    const long long i = m_pass * S + tile_k * TW + (long long)lane * L;  // first trajectory of this thread
+    const bool active = warp_active && i < N;              // N % L == 0 is guaranteed by the host
     const long long ic = active ? i : N - L;               // clamped index for per-trajectory parameter loads
-    const int s_warp = (int)((i0 + 32 * L * warp + prm.stream_offset) % S);  // first stream of this warp's tile
+    const int s_warp = (int)((tile_k * TW + prm.stream_offset) % S);  // first stream of the block's tile
     const int n_lab = kSummary ? (prm.truth ? 1 : 0) + (prm.nominal ? 1 : 0) : 0;
 
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + 3 * warp;  // warp-private: full[G0], full[G1], full[G2]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);  // full[G0], full[G1], full[G2]
+    int *consumed = reinterpret_cast<int *>(smem_raw + 64);   // warps that have finished reading the current copy of G0, G1, G2
     constexpr int kRefRows = kMpc ? TMA_CH_REF : 0;
-    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in() + warp * TmaSmem<Real>::warp_bytes(n_lab, kRefRows));
-    Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // this warp's [C][32] tiles (of Real)
+    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in());
+    Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // the block's [C][32] tiles (of Real)
     Real *refw = g2w + 12 * n_lab * 32;                              // reference body angles (kMpc), fetched with G0
     Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab, kRefRows));
     AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + TmaSmem<Real>::off_acc(n_lab, kRefRows)) + tid;
 
-    if (lane == 0) {
+    if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         mbar_init(&bars[2], 1);
+        consumed[0] = consumed[1] = consumed[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    if (prm.T > 0) {
+    __syncthreads();
+    if (!warp_active) return;  // fewer members than warps in the last group of a tile
+    if (prm.T > 0 && warp == 0) {  // warp 0 of a block always has work
         issue_g0<kMpc>(maps, 0, s_warp, g0w, refw, &bars[0], lane);
         issue_g1(maps, 0, s_warp, g1w, &bars[1], lane);
         if (n_lab) issue_g2(maps, 0, s_warp, n_lab, g2w, &bars[2], lane);
     }
+    // A warp is done with group g of this step; the LAST warp of the block to get here refills the group for the next step.
+    // (The counter is reset before the copy is issued, and nobody can count for the next step before that copy has landed.)
+    const auto last_reader = [&](int g) -> int {
+        __syncwarp();  // every lane of this warp has read its values
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = atomicAdd(&consumed[g], 1) == n_active - 1;
+            if (last) {
+                consumed[g] = 0;
+                __threadfence_block();
+            }
+        }
+        return last ? 0 : 1;  // 0 = "this lane issues the copy" in the issue_* helpers
+    };
 
     Real *q = noise + tid, *r = noise + 12 * nt + tid;
 #pragma unroll
@@ -293,8 +310,10 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
 #pragma unroll
                 for (int k = 0; k < 3; ++k) E[3 * a + k] = exp_minus_one(Real(prm.dt) * Rb[3 * k + a]);
         }
-        __syncwarp();  // every lane has consumed this step's feet and forces: refill G0 for step t + 1
-        if (more) issue_g0<kMpc>(maps, t + 1, s_warp, g0w, refw, &bars[0], lane);
+        {  // this warp has consumed the step's feet and forces: the last one refills G0 for step t + 1
+            const int elect = last_reader(0);
+            if (more) issue_g0<kMpc>(maps, t + 1, s_warp, g0w, refw, &bars[0], elect);
+        }
         if constexpr (kOut == 2) {
             if (active && prm.x_model_steps) {
 #pragma unroll
@@ -334,8 +353,10 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
         fold_pipelined<7, kBlock>(P, x, z[7 * 32], r[7 * nt], r[8 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
         fold_pipelined<8, kBlock>(P, x, z[8 * 32], r[8 * nt], r[9 * nt], inv, inv_n, nis, status, nothing); inv = inv_n;
         const Real z9 = z[9 * 32], r9 = r[9 * nt];
-        __syncwarp();  // every lane has read its last measurement of this step: refill G1 for step t + 1
-        if (more) issue_g1(maps, t + 1, s_warp, g1w, &bars[1], lane);
+        {  // this warp has read its last measurement of the step: the last one refills G1 for step t + 1
+            const int elect = last_reader(1);
+            if (more) issue_g1(maps, t + 1, s_warp, g1w, &bars[1], elect);
+        }
         fold_pipelined<9, kBlock>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
             // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
             rot_zyx(x[0], x[1], x[2], Rm);
@@ -377,8 +398,8 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
         if constexpr (kSummary) {
             acc_add(24, to_acc(nis));
             if (n_lab) {
-                __syncwarp();  // every lane has consumed this step's labels: refill G2 for step t + 1
-                if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], lane);
+                const int elect = last_reader(2);  // this warp has consumed the step's labels: the last one refills G2 for step t + 1
+                if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], elect);
             }
         }
     }

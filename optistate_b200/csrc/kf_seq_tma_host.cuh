@@ -57,9 +57,11 @@ int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t
     const size_t smem = TmaSmem<Real>::total(n_lab, kMpc ? TMA_CH_REF : 0, tma_acc_in_smem<Real, kSummary, kBlock>());
     auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc, kBlock>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
-    const long long per_block = (long long)TMA_THREADS * L;
-    const unsigned blocks = (unsigned)((p.N + per_block - 1) / per_block);
-    kern<<<blocks, TMA_THREADS, smem, stream>>>(p, maps);
+    // one block per (stream tile, group of TMA_WARPS members): see the index mapping at the top of the kernel
+    const long long tiles = p.S / (32 * L), n_pass = (p.N + p.S - 1) / p.S;
+    const long long blocks = tiles * ((n_pass + TMA_WARPS - 1) / TMA_WARPS);
+    if (blocks > 0x7fffffffLL) return OPTI_KF_E_SHAPE;
+    kern<<<(unsigned)blocks, TMA_THREADS, smem, stream>>>(p, maps);
     return OPTI_KF_OK;
 }
 
