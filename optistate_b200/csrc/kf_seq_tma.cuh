@@ -5,8 +5,8 @@
 //     [C] x 32 tiles of the [T*C][S] arrays, delivered by 2-D tensor-map copies (cp.async.bulk.tensor, SASS UTMALDG)
 //     per array - p, f, z, label streams - that complete on an mbarrier (complete_tx).  No per-thread address
 //     arithmetic, no LDG in the recursion, no registers tied up by loads in flight, no block-wide barrier.
-//   * The FOUR WARPS OF A BLOCK SHARE ONE TILE: they filter four different members (trajectory i, i + S, i + 2 S, i + 3 S)
-//     of the same 32 streams, so one copy feeds all of them and the block needs 15 KB of input tiles instead of 59 KB.
+//   * The WARPS OF A BLOCK SHARE ONE TILE: they filter different members (trajectory i, i + S, i + 2 S, ...) of the same 32
+//     streams, so one copy feeds all of them and a block of four needs 15 KB of input tiles instead of 59 KB.
 //     That is what decides occupancy: with a tile per warp the decoupled-group kernels (168 registers, three blocks per
 //     SM by registers) were held to two blocks by 108 KB of shared memory; with the shared tile three blocks fit
 //     (ncu: launch__occupancy_limit_shared_mem).  The warp that is LAST to finish reading a group (a shared-memory
@@ -36,8 +36,16 @@
 
 namespace okf {
 
-constexpr int TMA_THREADS = 128;
-constexpr int TMA_WARPS = TMA_THREADS / 32;
+// warps of a block = members that share one copy of a stream tile.  Four: the decoupled-group kernels then run 3 blocks = 12 warps
+// per SM at 166 registers.  Five warps x 3 blocks (15 warps per SM) fit the shared memory too, but cap the kernel at 128 registers:
+// measured 1.58e10 against 1.90e10 steps/s (FP64) and 2.9e10 against 3.6e10 (FP32) - the spills cost more than the warps bring.
+#ifndef OKF_BLK_WARPS
+#define OKF_BLK_WARPS 4
+#endif
+template <bool kBlock>
+__host__ __device__ constexpr int tma_warps() { return kBlock ? OKF_BLK_WARPS : 4; }
+template <bool kBlock>
+__host__ __device__ constexpr int tma_threads() { return 32 * tma_warps<kBlock>(); }
 constexpr int TMA_CH_G0 = 24, TMA_CH_G1 = 10;
 constexpr int TMA_CH_REF = 3;  // reference body angles of the predict_mpc covariance model (kMpc kernels), part of group G0
 constexpr int TMA_NOISE_ROWS = 22;  // q[12] r[10]
@@ -78,7 +86,7 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, 
                  : "memory");
 }
 
-template <typename Real>
+template <typename Real, int kThreads>
 struct TmaSmem {
     // dynamic shared memory: [mbarriers + counters 128 B][G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] (one tile
     //                        set per block)  [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
@@ -86,9 +94,9 @@ struct TmaSmem {
     static __host__ __device__ constexpr size_t warp_bytes(int n_lab, int ref_rows) { return warp_rows(n_lab, ref_rows) * 32 * sizeof(Real); }
     static __host__ __device__ constexpr size_t off_in() { return 128; }
     static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + warp_bytes(n_lab, ref_rows); }
-    static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)TMA_NOISE_ROWS * TMA_THREADS * sizeof(Real); }
+    static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)TMA_NOISE_ROWS * kThreads * sizeof(Real); }
     static __host__ __device__ constexpr size_t total(int n_lab, int ref_rows, bool acc_in_smem) {
-        return off_acc(n_lab, ref_rows) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * TMA_THREADS * 8 : 0);
+        return off_acc(n_lab, ref_rows) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * kThreads * 8 : 0);
     }
 };
 
@@ -143,7 +151,7 @@ __host__ __device__ constexpr bool tma_acc_in_smem() {
 }
 
 template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock = false>
-__global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kBlock>()) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
+__global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kSummary, kBlock>()) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
     using AccT = typename Acc<Real>::type;
@@ -151,11 +159,12 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
     static_assert(!(kBlock && kMpc), "the element-wise exponential of predict_mpc couples every state");
     constexpr bool kAccSmem = tma_acc_in_smem<Real, kSummary, kBlock>();  // double / F2 with the full P: the 25 running sums do not fit next to P in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int nt = TMA_THREADS;
+    constexpr int nt = tma_threads<kBlock>(), TMA_WARPS = tma_warps<kBlock>();
+    using Smem = TmaSmem<Real, nt>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = prm.N, S = prm.S;
-    // Block (tile k, group j) filters members 4 j .. 4 j + 3 of the 32 L streams of tile k: warp w owns trajectories
-    // (4 j + w) S + 32 L k + L lane (+ 0 .. L-1), which all read stream tile k (shifted by the stream offset).  Blocks of one
+    // Block (tile k, group j) filters members W j .. W j + W - 1 of the 32 L streams of tile k (W = warps of the block): warp w owns
+    // trajectories (W j + w) S + 32 L k + L lane (+ 0 .. L-1), which all read stream tile k (shifted by the stream offset).  Blocks of one
     // tile are launched next to each other, so the tile's whole time series (tens of MB) stays L2-resident however far the
     // resident blocks drift apart in time (measured in round 1: 375 GB -> ~1 GB of DRAM reads per launch on the 1 M x 1 k sweep).
     constexpr int TW = 32 * L;                                     // streams of a tile = trajectories of a warp
@@ -174,11 +183,11 @@ __global__ void __launch_bounds__(TMA_THREADS, tma_min_blocks<Real, kSummary, kB
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);  // full[G0], full[G1], full[G2]
     int *consumed = reinterpret_cast<int *>(smem_raw + 64);   // warps that have finished reading the current copy of G0, G1, G2
     constexpr int kRefRows = kMpc ? TMA_CH_REF : 0;
-    Real *g0w = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_in());
+    Real *g0w = reinterpret_cast<Real *>(smem_raw + Smem::off_in());
     Real *g1w = g0w + TMA_CH_G0 * 32, *g2w = g1w + TMA_CH_G1 * 32;  // the block's [C][32] tiles (of Real)
     Real *refw = g2w + 12 * n_lab * 32;                              // reference body angles (kMpc), fetched with G0
-    Real *noise = reinterpret_cast<Real *>(smem_raw + TmaSmem<Real>::off_noise(n_lab, kRefRows));
-    AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + TmaSmem<Real>::off_acc(n_lab, kRefRows)) + tid;
+    Real *noise = reinterpret_cast<Real *>(smem_raw + Smem::off_noise(n_lab, kRefRows));
+    AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + Smem::off_acc(n_lab, kRefRows)) + tid;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);

@@ -54,14 +54,15 @@ int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t
     if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw, 12);
     if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw, 12);
     if (!ok) return 1;
-    const size_t smem = TmaSmem<Real>::total(n_lab, kMpc ? TMA_CH_REF : 0, tma_acc_in_smem<Real, kSummary, kBlock>());
+    constexpr int kThreads = tma_threads<kBlock>(), kWarps = tma_warps<kBlock>();
+    const size_t smem = TmaSmem<Real, kThreads>::total(n_lab, kMpc ? TMA_CH_REF : 0, tma_acc_in_smem<Real, kSummary, kBlock>());
     auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc, kBlock>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
-    // one block per (stream tile, group of TMA_WARPS members): see the index mapping at the top of the kernel
+    // one block per (stream tile, group of kWarps members): see the index mapping at the top of the kernel
     const long long tiles = p.S / (32 * L), n_pass = (p.N + p.S - 1) / p.S;
-    const long long blocks = tiles * ((n_pass + TMA_WARPS - 1) / TMA_WARPS);
+    const long long blocks = tiles * ((n_pass + kWarps - 1) / kWarps);
     if (blocks > 0x7fffffffLL) return OPTI_KF_E_SHAPE;
-    kern<<<(unsigned)blocks, TMA_THREADS, smem, stream>>>(p, maps);
+    kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p, maps);
     return OPTI_KF_OK;
 }
 

@@ -1,0 +1,3 @@
+timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_peer_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline --no-secondary --no-e2e | cut -c1-330
+timeout 300 python bench.py --dtype f32 --no-secondary --no-cpu-baseline --no-e2e | cut -c1-200
