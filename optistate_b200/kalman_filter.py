@@ -73,60 +73,68 @@ class Kalman_Filter:
     def _col(a, n):
         return np.asarray(a, dtype=np.float64).reshape(n)
 
-    def _step(self, phases, cov_model, host_in, want):
-        """One trajectory, one step through optistate_kf_batch (JOINT).  host_in / outputs are packed into one
-        host->device and one device->host copy."""
+    # One pinned host buffer and one device buffer each way, allocated once per instance: a call is then one asynchronous
+    # host->device copy, one launch, two asynchronous device->host copies (values, status) and ONE stream synchronisation,
+    # issued by the binding (kf_host_call) below the Python dispatcher - no allocation, no pageable staging copy, no
+    # device-side concatenation (which cost the first version ~110 us per call).
+    _IN_MAX = 12 + 144 + 144 + 100 + 12 + 12 + 12 + 10 + 6 + 12 + 4
+    _OUT_SIZES = {"x_final": 12, "P_final": 144, "K_final": 120, "p_world_steps": 12, "p_trace_steps": 1, "k_gain_steps": 1, "odom": 4}
+    _OUT_MAX = 12 + 144 + 120 + 12 + 1 + 1 + 4
+
+    def _buffers(self):
         dev = self._dev()
-        ext = nv.ext()
-        names = list(host_in)
-        sizes = [host_in[k].size for k in names]
-        packed = torch.from_numpy(np.concatenate([np.ascontiguousarray(host_in[k], dtype=np.float64).reshape(-1) for k in names]))
-        dbuf = packed.to(dev)
-        tensors, off = {}, 0
-        for k, n in zip(names, sizes):
-            tensors[k] = dbuf[off:off + n]
+        if getattr(self, "_buf_dev", None) != dev:
+            self._buf_dev = dev
+            self._h_in = torch.empty(self._IN_MAX, dtype=torch.float64).pin_memory()
+            self._h_in_np = self._h_in.numpy()
+            self._d_in = torch.empty(self._IN_MAX, dtype=torch.float64, device=dev)
+            self._d_out = torch.empty(self._OUT_MAX, dtype=torch.float64, device=dev)
+            self._h_out = torch.empty(self._OUT_MAX, dtype=torch.float64).pin_memory()
+            self._h_out_np = self._h_out.numpy()
+            self._d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._h_status_np = self._h_status.numpy()
+        return dev
+
+    def _launch(self, host_in, want, cfg, consts):
+        """Packs `host_in` (name -> array, in order) into the pinned buffer; the binding uploads, launches (kf_batch with `cfg`, or
+        kf_measure when cfg is empty), downloads the `want` outputs and the status word and synchronises.  Returns {name: NumPy copy}."""
+        self._buffers()
+        in_layout, off = [], 0
+        for k, v in host_in.items():
+            n = v.size
+            self._h_in_np[off:off + n] = v.reshape(-1)
+            in_layout.append((k, n))
             off += n
-        out_sizes = {"x_final": 12, "P_final": 144, "K_final": 120, "p_world_steps": 12, "p_trace_steps": 1, "k_gain_steps": 1}
-        obuf = torch.empty(sum(out_sizes[k] for k in want), dtype=torch.float64, device=dev)
-        off = 0
-        for k in want:
-            tensors[k] = obuf[off:off + out_sizes[k]]
-            off += out_sizes[k]
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
-        tensors["status"] = status
-        cfg = dict(dtype=nv.F64, algo=nv.ALGO_JOINT, cov_model=cov_model, phases=phases, n_traj=1, n_steps=1, n_streams=1,
-                   x0_per_traj=0, p0_kind=nv.MAT_DENSE, q_kind=nv.MAT_DENSE, r_kind=nv.MAT_DENSE)
-        with torch.cuda.device(dev):
-            nv.check(ext.kf_batch(cfg, self._consts(), tensors), "optistate_kf_batch")
-        host = torch.cat([obuf, status.to(torch.float64)]).cpu().numpy()
+        out_layout = [(k, self._OUT_SIZES[k]) for k in want]
+        nv.check(int(nv.ext().kf_host_call(cfg, consts, in_layout, out_layout, self._h_in, self._d_in, self._d_out, self._h_out,
+                                            self._d_status, self._h_status)), "optistate_kf_batch" if cfg else "optistate_kf_measure")
+        self.status = int(self._h_status_np[0])
         res, off = {}, 0
-        for k in want:
-            res[k] = host[off:off + out_sizes[k]].copy()
-            off += out_sizes[k]
-        self.status = int(host[-1])
+        for k, n in out_layout:
+            res[k] = self._h_out_np[off:off + n].copy()
+            off += n
         return res
 
+    def _step(self, phases, cov_model, host_in, want):
+        """One trajectory, one step through optistate_kf_batch (JOINT)."""
+        cfg = dict(dtype=nv.F64, algo=nv.ALGO_JOINT, cov_model=cov_model, phases=phases, n_traj=1, n_steps=1, n_streams=1,
+                   x0_per_traj=0, p0_kind=nv.MAT_DENSE, q_kind=nv.MAT_DENSE, r_kind=nv.MAT_DENSE)
+        return self._launch(host_in, want, cfg, self._consts())
+
     def _state_in(self):
-        return {"x0": self._col(self.x, 12), "P0": np.asarray(self.P, float).reshape(144),
-                "Q": np.asarray(self.Q, float).reshape(144), "R": np.asarray(self.R, float).reshape(100)}
+        return {"x0": self._col(self.x, 12), "P0": np.asarray(self.P, dtype=np.float64).reshape(144),
+                "Q": np.asarray(self.Q, dtype=np.float64).reshape(144), "R": np.asarray(self.R, dtype=np.float64).reshape(100)}
 
     # ------------------------------------------------------------------ reference surface
     def get_odom(self, p_cur, dp_cur, contact_cur, imu):
         """kalman_filter.py:79-105 -> (4,1) array [z, vx, vy, vz]."""
-        dev = self._dev()
-        ext = nv.ext()
-        host = np.concatenate([self._col(imu, 6), self._col(p_cur, 12), self._col(dp_cur, 12), self._col(contact_cur, 4)])
-        dbuf = torch.from_numpy(host).to(dev)
-        tensors = {"imu": dbuf[0:6], "p": dbuf[6:18], "dp": dbuf[18:30], "contact": dbuf[30:34],
-                   "odom": torch.empty(4, dtype=torch.float64, device=dev),
-                   "status": torch.zeros(1, dtype=torch.int32, device=dev)}
-        with torch.cuda.device(dev):
-            nv.check(ext.kf_measure(nv.F64, 1, 1, tensors), "optistate_kf_measure")
-        out = torch.cat([tensors["odom"], tensors["status"].to(torch.float64)]).cpu().numpy()
-        if int(out[4]) & nv.ST_ALL_SWING:
+        host_in = {"imu": self._col(imu, 6), "p": self._col(p_cur, 12), "dp": self._col(dp_cur, 12), "contact": self._col(contact_cur, 4)}
+        r = self._launch(host_in, ["odom"], {}, {})
+        if self.status & nv.ST_ALL_SWING:
             raise ValueError("setting an array element with a sequence. The requested array has an inhomogeneous shape "
                              "(all four feet in swing; the reference fails here too, kalman_filter.py:97-103)")
-        return out[0:4].reshape(4, 1).copy()
+        return r["odom"].reshape(4, 1)
 
     def set_measurements(self, imu, odom):
         """kalman_filter.py:108-117 (in-place scatter into self.z)."""

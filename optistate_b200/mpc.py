@@ -84,7 +84,8 @@ class WarmStart:
 
 
 def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=None, R=None, *, dt: float = INITIAL_PARAMS.DT_mpc,
-                             mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None, gravity: float = INITIAL_PARAMS.GRAVITY, **mpc_kw):
+                             mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None, gravity: float = INITIAL_PARAMS.GRAVITY,
+                             return_p_world: bool = False, **mpc_kw):
     """The reference's closed loop `KF.estimate_state_mpc(imu, p, dp, body_ref, contact)` (kalman_filter.py:176-182) for N
     trajectories over T steps, everything on the device: at every step the force MPC is solved for each trajectory from
     its CURRENT state estimate, then one filter step runs with those forces and the predict_mpc covariance model.
@@ -93,7 +94,9 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     filter's transition uses its first column, as the class does).  x0, P0, Q, R as in kf_batch (P0 None = Q); dense Q / R or a
     non-symmetric P0 run the filter step in its joint form, like the class.  dt, mass, inertia, gravity are the model constants
     of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs, solver, warm) goes to mpc_forces only.
-    Returns (x_steps [T,12,N], forces [T,12,N] - the applied stage-0 forces -, mpc_status [T,N], filter status [N]).
+    Returns (x_steps [T,12,N], forces [T,12,N] - the applied stage-0 forces -, mpc_status [T,N], filter status [N]) and, with
+    return_p_world, the feet rotated into the world frame [T,12,N] (the reference's in-place mutation of p, which its driver
+    writes into the GRU feature rows).
     """
     from .batch import _as_device, _noise, kf_batch
 
@@ -107,6 +110,8 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     fs = torch.empty((T, 12, N), dtype=torch.float64, device=device)
     mst = torch.empty((T, N), dtype=torch.int32, device=device)
     fst = torch.zeros(N, dtype=torch.int32, device=device)
+    pws = torch.empty((T, 12, N), dtype=torch.float64, device=device) if return_p_world else None
+    outputs = ("x_final", "P_final", "p_world_steps") if return_p_world else ("x_final", "P_final")
     # everything that would make a step synchronise with the host is settled once, before the loop: the classification of the
     # noise arguments (a dense matrix that is exactly diagonal becomes a diagonal), the symmetry of the initial P, the bound
     # on the legs out of swing over all steps
@@ -129,10 +134,12 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
         forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **model, **mpc_kw)
         fs[t], mst[t] = forces[0], st
         res = kf_batch(imu[t:t + 1], p[t:t + 1], dp[t:t + 1], contact[t:t + 1], forces[0:1], x0=x, P0=Pm, Q=q_t, R=r_t, n_traj=N,
-                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=("x_final", "P_final"), algo=algo, q_kind=q_kind, r_kind=r_kind,
+                       cov_model="mpc", body_ref=body_ref[t, 0:1], outputs=outputs, algo=algo, q_kind=q_kind, r_kind=r_kind,
                        p0_kind=p_kind, p0_is_symmetric=p_sym, **model)
         # the fed-back covariance: dense per trajectory; symmetric by construction on the packed-symmetric path
         x, Pm, p_kind = res.x_final, res.P_final, nv.MAT_DENSE_PER
         xs[t] = x
+        if return_p_world:
+            pws[t] = res.p_world_steps[0]
         fst |= res.status
-    return xs, fs, mst, fst
+    return (xs, fs, mst, fst, pws) if return_p_world else (xs, fs, mst, fst)
