@@ -87,11 +87,17 @@ enum { OPTI_KF_FLAG_P0_DECOUPLED = 1, OPTI_KF_FLAG_FULL_COVARIANCE = 2 };
 
 /* status[i] bits */
 enum {
-    OPTI_KF_ST_NOT_PD = 1,     /* a pivot of S was <= 0 or not finite (reference: LinAlgError / garbage)      */
+    OPTI_KF_ST_NOT_PD = 1,     /* a pivot of S was <= 0 or not finite: S is not positive definite.  SEQUENTIAL carries on
+                                  with that pivot; JOINT switches to the pivoted inverse the reference uses            */
     OPTI_KF_ST_NONFINITE = 2,  /* a state became inf/nan                                                        */
+    /* (Angles: sin / cos use a two-term Cody-Waite reduction, <= 1 ulp for |angle| <= 2e5 rad in FP64 and <= 8e3 rad in FP32 -
+     *  thousands of turns; attitudes beyond that lose accuracy gradually and may flip the trunc(R^T) decision of
+     *  force_controller.py:271 relative to NumPy.  Physical attitudes are within a few radians.)                              */
     OPTI_KF_ST_ALL_SWING = 4,  /* a step had sum(contact) == 0 (reference raises ValueError, kalman_filter.py:97-103);
                                   the odometry part of z is set to 0 for that step                              */
-    OPTI_KF_ST_ASYMMETRIC = 8  /* JOINT: S was visibly asymmetric; the Cholesky solve used its lower triangle   */
+    OPTI_KF_ST_ASYMMETRIC = 8, /* JOINT: S was visibly asymmetric: pivoted inverse instead of the Cholesky solve */
+    OPTI_KF_ST_SINGULAR = 16   /* JOINT: the pivoted inverse of S met a zero pivot - where the reference's np.linalg.inv raises
+                                  LinAlgError (kalman_filter.py:168); an indefinite but regular S does not set it       */
 };
 
 /* error codes */

@@ -90,6 +90,17 @@ def _stream_tensor(a, C, name, dtype, device):
     return t.contiguous(), t.shape[0], t.shape[2]
 
 
+def _checked_stream_index(stream_index, N: int, S: int, device) -> torch.Tensor:
+    """The kernels use the entries as gather offsets, so they are range-checked here (one small reduction; the gather path is not
+    the streamed hot path)."""
+    t = _as_device(stream_index, torch.int32, device).reshape(N)
+    if N > 0:
+        lo, hi = (int(v) for v in torch.aminmax(t))
+        if lo < 0 or hi >= S:
+            raise ValueError(f"stream_index entries must lie in [0, {S}), got [{lo}, {hi}]")
+    return t
+
+
 def _is_diagonal(m: torch.Tensor) -> bool:
     return bool(torch.count_nonzero(m - torch.diag(torch.diagonal(m))) == 0)
 
@@ -190,7 +201,7 @@ def kf_batch(
                 if not bool(torch.count_nonzero(m[_CROSS_GROUP.to(device)])):
                     flags |= nv.FLAG_P0_DECOUPLED
     if stream_index is not None:
-        tensors["stream_index"] = _as_device(stream_index, torch.int32, device).reshape(N)
+        tensors["stream_index"] = _checked_stream_index(stream_index, N, S, device)
 
     want = []
     for o in outputs:

@@ -373,7 +373,9 @@ int optistate_kf_features(const OptiKfFeatureDesc *d, void *cuda_stream) {
     if (!d) return OPTI_KF_E_NULL;
     if (d->struct_size != sizeof(OptiKfFeatureDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
     if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
-    if (d->n_traj < 0 || d->n_steps < 0 || d->n_streams <= 0 || d->n_steps > 65535) return OPTI_KF_E_SHAPE;
+    if (d->n_traj < 0 || d->n_steps < 0 || d->n_streams <= 0) return OPTI_KF_E_SHAPE;
+    if ((d->n_steps + okf::FEAT_STEPS - 1) / okf::FEAT_STEPS > 65535) return OPTI_KF_E_SHAPE;  // grid.y
+    if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     if (!d->x_steps || !d->p_world_steps || !d->imu || !d->f || !d->dp || !d->rows) return OPTI_KF_E_NULL;
     if (d->n_traj == 0 || d->n_steps == 0) return OPTI_KF_OK;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -393,7 +395,13 @@ int optistate_kf_features(const OptiKfFeatureDesc *d, void *cuda_stream) {
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
 }
 
-static const int kMinmaxBlocks = 592;
+static const int kMinmaxBlocks = 592;  // upper bound (sizes the scratch buffer); the launch takes 4 blocks per SM of the current device
+// multiprocessors of the current device (launch geometry is derived from it, not from the B200's 148)
+static int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
+}
 
 size_t optistate_kf_minmax_scratch_bytes(int dtype, int32_t n_cols) {
     return (size_t)kMinmaxBlocks * 2 * (size_t)(n_cols > 0 ? n_cols : 0) * (dtype == OPTI_KF_F64 ? 8 : 4);
@@ -406,12 +414,13 @@ int optistate_kf_minmax(int dtype, const void *rows, int64_t n_rows, int32_t n_c
     if (n_rows <= 0 || n_cols <= 0 || n_cols > 256 || scratch_bytes < optistate_kf_minmax_scratch_bytes(dtype, n_cols)) return OPTI_KF_E_SHAPE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     cudaGetLastError();
+    const int nblk = 4 * sm_count() < kMinmaxBlocks ? 4 * sm_count() : kMinmaxBlocks;
     if (dtype == OPTI_KF_F64) {
-        okf::kf_minmax_partial_kernel<double><<<kMinmaxBlocks, 256, 2 * 256 * sizeof(double), stream>>>((const double *)rows, n_rows, n_cols, (double *)scratch);
-        okf::kf_minmax_final_kernel<double><<<1, 256, 0, stream>>>((const double *)scratch, kMinmaxBlocks, n_cols, (double *)min_out, (double *)max_out);
+        okf::kf_minmax_partial_kernel<double><<<nblk, 256, 2 * 256 * sizeof(double), stream>>>((const double *)rows, n_rows, n_cols, (double *)scratch);
+        okf::kf_minmax_final_kernel<double><<<1, 256, 0, stream>>>((const double *)scratch, nblk, n_cols, (double *)min_out, (double *)max_out);
     } else {
-        okf::kf_minmax_partial_kernel<float><<<kMinmaxBlocks, 256, 2 * 256 * sizeof(float), stream>>>((const float *)rows, n_rows, n_cols, (float *)scratch);
-        okf::kf_minmax_final_kernel<float><<<1, 256, 0, stream>>>((const float *)scratch, kMinmaxBlocks, n_cols, (float *)min_out, (float *)max_out);
+        okf::kf_minmax_partial_kernel<float><<<nblk, 256, 2 * 256 * sizeof(float), stream>>>((const float *)rows, n_rows, n_cols, (float *)scratch);
+        okf::kf_minmax_final_kernel<float><<<1, 256, 0, stream>>>((const float *)scratch, nblk, n_cols, (float *)min_out, (float *)max_out);
     }
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError() == cudaSuccess ? OPTI_KF_OK : OPTI_KF_E_CUDA;
@@ -434,7 +443,7 @@ int optistate_kf_windows(int dtype, const void *rows, const float *latent, const
     const int width = n_cols + n_latent;
     float *full = (float *)scratch;
     cudaGetLastError();
-    const unsigned nb = 148 * 16;
+    const unsigned nb = (unsigned)sm_count() * 16;
     if (dtype == OPTI_KF_F64)
         okf::kf_normalise_rows_kernel<double><<<nb, 256, 0, stream>>>((const double *)rows, latent, (const double *)mn, (const double *)mx,
                                                                       n_rows, n_cols, n_latent, full);
@@ -460,6 +469,7 @@ int optistate_kf_identify_noise(const OptiKfIdentifyDesc *d, void *cuda_stream) 
     if (d->struct_size != sizeof(OptiKfIdentifyDesc) || d->abi_version != OPTISTATE_KF_ABI_VERSION) return OPTI_KF_E_VERSION;
     if (d->dtype != OPTI_KF_F64 && d->dtype != OPTI_KF_F32) return OPTI_KF_E_DTYPE;
     if (d->n_traj <= 0 || d->n_steps < 2 || d->n_streams <= 0) return OPTI_KF_E_SHAPE;
+    if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     if (!(d->dt > 0) || !(d->mass > 0) || !(d->inertia[0] > 0) || !(d->inertia[1] > 0) || !(d->inertia[2] > 0)) return OPTI_KF_E_SHAPE;
     if (!d->gt || !d->imu || !d->p || !d->dp || !d->contact || !d->f || !d->q_diag || !d->r_diag || !d->scratch) return OPTI_KF_E_NULL;
     if (d->scratch_bytes < optistate_kf_identify_scratch_bytes(d->dtype, d->n_traj, d->n_steps)) return OPTI_KF_E_SHAPE;

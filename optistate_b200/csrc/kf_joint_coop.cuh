@@ -346,14 +346,20 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
 #pragma unroll
             for (int j = 0; j < NZ; ++j) y[j] = z[j] - x[sel(j)];
 
-            if (!asym) {
+            // A symmetric S is factorised by Cholesky.  If that breaks down (S indefinite: only a user-supplied non-PSD P / R gets
+            // there) the strict lower triangle, which the factorisation has overwritten, is restored from the upper one and the
+            // trajectory takes the pivoted inverse like a visibly asymmetric S does - the reference's np.linalg.inv raises for a
+            // SINGULAR S only and carries on with an indefinite one (kalman_filter.py:168).
+            bool lu = asym != 0;
+            if (!lu) {
                 // cooperative Cholesky, in place in the lower triangle of LM; dinv[j] = 1 / L[j][j] in VC
+                bool broke = false;
 #pragma unroll
                 for (int j = 0; j < NZ; ++j) {
                     Real d = LM(j * NZ + j);
 #pragma unroll
                     for (int k = 0; k < j; ++k) d -= LM(j * NZ + k) * LM(j * NZ + k);
-                    if (!(d > Real(0)) || !(d < Real(3e38))) status |= OPTI_KF_ST_NOT_PD;
+                    if (!(d > Real(0)) || !(d < Real(3e38))) broke = true;  // -> OPTI_KF_ST_NOT_PD, and the pivoted inverse below
                     const Real dinv = rsqrt(d);  // 1 / L[j][j]
 #pragma unroll
                     for (int rr = 0; rr < 3; ++rr) {
@@ -368,6 +374,22 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                     if (q == 0) VC(j) = dinv;
                     quad_sync();
                 }
+                if (broke) {  // quad-uniform: every lane evaluates the same pivots
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) {
+                        const int a = q + 4 * rr;
+                        if (a < NZ) {
+#pragma unroll
+                            for (int b = 0; b < NZ; ++b)
+                                if (b < a) LM(a * NZ + b) = LM(b * NZ + a);
+                        }
+                    }
+                    quad_sync();
+                    lu = true;
+                    status |= OPTI_KF_ST_NOT_PD;
+                }
+            }
+            if (!lu) {
                 // NIS = |L^-1 y|^2 (replicated) and the three K rows of this lane: L u = P[i,sel]^T, then L^T k = u
                 {
                     Real u[NZ];
@@ -403,8 +425,8 @@ __global__ void __launch_bounds__(JC_THREADS, sizeof(Real) == 4 ? 3 : 2) kf_join
                     Kr[0][j] = v0 * dj; Kr[1][j] = v1 * dj; Kr[2][j] = v2 * dj;
                 }
             } else {
-                status |= OPTI_KF_ST_ASYMMETRIC;
-                if (q == 0 && invert10_inplace(lm_)) status |= OPTI_KF_ST_NOT_PD;
+                if (asym) status |= OPTI_KF_ST_ASYMMETRIC;
+                if (q == 0 && invert10_inplace(lm_)) status |= OPTI_KF_ST_NOT_PD | OPTI_KF_ST_SINGULAR;
                 quad_sync();
 #pragma unroll
                 for (int a = 0; a < NZ; ++a) {

@@ -33,7 +33,9 @@ def assemble_features(x_steps: torch.Tensor, p_world_steps: torch.Tensor, imu, f
     if imu_acc is not None:
         tensors["imu_acc"] = as_dev(imu_acc)
     if stream_index is not None:
-        tensors["stream_index"] = torch.as_tensor(stream_index).to(device=dev, dtype=torch.int32).contiguous()
+        from .batch import _checked_stream_index
+
+        tensors["stream_index"] = _checked_stream_index(stream_index, N, S, dev)
     with torch.cuda.device(dev):
         nv.check(nv.ext().kf_features(_code(dtype), N, T, S, int(stream_offset), tensors), "optistate_kf_features")
     return tensors["rows"]

@@ -30,7 +30,9 @@ def identify_noise(gt, imu, p, dp, contact, f, *, n_traj=None, dtype: torch.dtyp
     tensors["r_diag"] = torch.empty((10, N), dtype=dtype, device=device)
     tensors["status"] = torch.zeros(N, dtype=torch.int32, device=device)
     if stream_index is not None:
-        tensors["stream_index"] = torch.as_tensor(stream_index).to(device=device, dtype=torch.int32).contiguous()
+        from .batch import _checked_stream_index
+
+        tensors["stream_index"] = _checked_stream_index(stream_index, N, S, device)
     inertia = np.diag(INITIAL_PARAMS.INERTIA_ROT) if inertia is None else np.asarray(inertia, float).reshape(3)
     consts = dict(dt=float(dt), mass=float(mass), inertia0=float(inertia[0]), inertia1=float(inertia[1]), inertia2=float(inertia[2]),
                   gravity=float(gravity))

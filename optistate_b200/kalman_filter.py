@@ -55,6 +55,16 @@ class Kalman_Filter:
         self.F_d = self.identity_large + self.dt * self.F
         self.B_d = self.dt * self.B
         self.f = np.zeros((12, 1))
+        # attributes of the reference's MPC set-up (kalman_filter.py:58-77).  The QP lives on the device (optistate_b200.mpc), so
+        # there is no CasADi StanceController object behind `stance_controller`; the horizon buffers keep the reference's shapes
+        # and are filled by predict_mpc as the reference fills them (kalman_filter.py:141-146).
+        self.stance_controller = None
+        self.p_mpc = np.zeros((12, 6))
+        self.body_mpc = np.zeros((12, 6))
+        self.contact_mpc = np.zeros((4, 5))
+        self.zero_mat = np.zeros((3, 3))
+        self.identity = np.eye(3)
+        self.identity_m = np.eye(3) / self.m
         self.force_provider = force_provider
         self.status = 0
         self._device = device
@@ -180,6 +190,10 @@ class Kalman_Filter:
                                         gravity=float(np.asarray(self.g, float).reshape(12)[11]), device=self._dev())
                 self.mpc_status = int(st[0])
                 f = forces[:, :, 0].cpu().numpy().T  # (12, horizon) like sol.value(controls), kalman_filter.py:152
+        self.p_mpc[:] = np.asarray(p, float).reshape(12, 1)                 # kalman_filter.py:141-146
+        self.body_mpc[:, 0] = np.asarray(self.x, float).reshape(12)
+        self.body_mpc[:, 1:] = np.asarray(body_ref, float).reshape(12, -1)
+        self.contact_mpc[:] = np.asarray(cur_contact, float).reshape(4, 1)
         f = np.asarray(f, float)
         self.f = f if f.ndim == 2 and f.shape[1] > 1 else f.reshape(12, 1)
         f0 = self.f[:, 0].reshape(12)
@@ -197,7 +211,7 @@ class Kalman_Filter:
         """kalman_filter.py:164-174."""
         host_in = dict(self._state_in(), z_in=self._col(self.z, 10))
         r = self._step(nv.PHASE_UPDATE, nv.COV_PREDICT, host_in, ["x_final", "P_final", "K_final", "p_trace_steps", "k_gain_steps"])
-        if self.status & nv.ST_NOT_PD:
+        if self.status & nv.ST_SINGULAR:  # np.linalg.inv raises for a singular S only; an indefinite one goes through (kalman_filter.py:168)
             raise np.linalg.LinAlgError("Singular matrix")
         self.K = r["K_final"].reshape(12, 10)
         self.x = r["x_final"].reshape(12, 1)

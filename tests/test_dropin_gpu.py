@@ -93,3 +93,20 @@ def test_error_conventions():
     kf.R = np.zeros((10, 10))
     with pytest.raises(np.linalg.LinAlgError):  # singular S (kalman_filter.py:168)
         kf.update()
+    # an INDEFINITE but regular S does not raise in the reference (np.linalg.inv only fails on an exactly singular matrix): the
+    # device path takes the pivoted inverse there too and returns the reference's numbers
+    kf3 = Kalman_Filter()
+    kf3.x = np.arange(12, dtype=float).reshape(12, 1) * 0.01
+    kf3.P = np.diag(np.linspace(0.01, 0.02, 12))
+    kf3.R = np.diag([0.01, 0.01, 0.01, -1.0, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01])
+    kf3.z = np.linspace(-0.1, 0.1, 10).reshape(10, 1)
+    H = np.asarray(kf3.H, float)
+    S = H @ kf3.P @ H.T + kf3.R
+    K = kf3.P @ H.T @ np.linalg.inv(S)
+    want_x = kf3.x + K @ (kf3.z - H @ kf3.x)
+    want_P = (np.eye(12) - K @ H) @ kf3.P
+    kf3.update()
+    assert np.abs(kf3.x - want_x).max() < 1e-12 and np.abs(kf3.P - want_P).max() < 1e-13 and np.abs(kf3.K - K).max() < 1e-12
+    # the attributes of the reference's MPC set-up exist with its shapes (kalman_filter.py:37-43,73-77)
+    assert kf3.p_mpc.shape == (12, 6) and kf3.body_mpc.shape == (12, 6) and kf3.contact_mpc.shape == (4, 5)
+    assert kf3.zero_mat.shape == (3, 3) and np.array_equal(kf3.identity, np.eye(3)) and np.allclose(kf3.identity_m, np.eye(3) / kf3.m)
