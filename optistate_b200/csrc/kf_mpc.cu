@@ -25,10 +25,19 @@ int launch_mpc(const MpcParams &p, cudaStream_t stream) {
         kf_mpc_rows_kernel<<<blocks, 32 * MPCR_WARPS, smem, stream>>>(q);
         return OPTI_KF_OK;
     }
+    // three or four legs out of swing somewhere in the batch: the dual active set with two warps per problem (kf_mpc_gi.cuh), then
+    // the round-1 shared-memory interior point (kf_mpc.cuh) for what it flags - or for everything on request / without a status array
+    MpcParams q = p;
+    if (p.solver == 0 && p.status != nullptr) {
+        const size_t smem2 = mpcg2_smem_bytes(p.max_legs);
+        if (cudaFuncSetAttribute(kf_mpc_gi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) return OPTI_KF_E_CUDA;
+        kf_mpc_gi2_kernel<<<(unsigned)p.N, 64, smem2, stream>>>(p);
+        q.only_flagged = 1;
+    }
     const size_t smem = mpc_smem_bytes(p.max_legs);
     if (cudaFuncSetAttribute(kf_mpc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     const unsigned blocks = (unsigned)((p.N + MPC_WARPS - 1) / MPC_WARPS);
-    kf_mpc_kernel<<<blocks, 32 * MPC_WARPS, smem, stream>>>(p);
+    kf_mpc_kernel<<<blocks, 32 * MPC_WARPS, smem, stream>>>(q);
     return OPTI_KF_OK;
 }
 

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(32 * MPC_WARPS) kf_mpc_kernel(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long prob = (long long)blockIdx.x * MPC_WARPS + warp;
     if (prob >= prm.N) return;  // whole warp
+    if (prm.only_flagged && prm.status[prob] != MPC_ST_GIVEN_UP) return;  // second launch behind the dual active-set kernel
     const int nmax = 15 * prm.max_legs, ld = nmax;  // ld: row stride of the sensitivities
     double *base = reinterpret_cast<double *>(smem_raw) + (size_t)warp * mpc_warp_doubles(prm.max_legs);
     double *H = base, *M = base + mpc_mat_doubles(prm.max_legs);

@@ -141,17 +141,76 @@ struct MpcRows {
     }
 };
 
+// The threads that work on one problem: one warp, or - for the orders 45 and 60 of three and four legs out of swing in
+// kf_mpc_gi.cuh - the two warps of a 64-thread block.  Thread t of the group owns row t / slot t / constraint block t.
+// `scr`: eight doubles of shared memory per problem (only the two-warp form touches it).
+__device__ __forceinline__ void warp_argmin(double &v, int &idx) {  // smallest (value, index); ties to the smaller index; index < 0 = none
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (oi >= 0 && (idx < 0 || ov < v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+    }
+}
+template <int NW>
+struct MpcGroup;
+template <>
+struct MpcGroup<1> {
+    static constexpr int threads = 32;
+    static __device__ __forceinline__ int tid() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ double sum(double v, double *) { return warp_sum(v); }
+    static __device__ __forceinline__ double max(double v, double *) { return warp_max(v); }
+    static __device__ __forceinline__ void argmin(double &v, int &idx, double *) { warp_argmin(v, idx); }
+};
+template <>
+struct MpcGroup<2> {  // one problem per 64-thread block
+    static constexpr int threads = 64;
+    static __device__ __forceinline__ int tid() { return threadIdx.x; }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ double sum(double v, double *scr) {
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = scr[0] + scr[1];
+        __syncthreads();
+        return v;
+    }
+    static __device__ __forceinline__ double max(double v, double *scr) {
+        v = warp_max(v);
+        if ((threadIdx.x & 31) == 0) scr[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = fmax(scr[0], scr[1]);
+        __syncthreads();
+        return v;
+    }
+    static __device__ __forceinline__ void argmin(double &v, int &idx, double *scr) {
+        warp_argmin(v, idx);
+        if ((threadIdx.x & 31) == 0) {
+            scr[2 + 2 * (threadIdx.x >> 5)] = v;
+            scr[3 + 2 * (threadIdx.x >> 5)] = (double)idx;
+        }
+        __syncthreads();
+        const double v0 = scr[2], v1 = scr[4];
+        const int i0 = (int)scr[3], i1 = (int)scr[5];
+        const bool second = i1 >= 0 && (i0 < 0 || v1 < v0 || (v1 == v0 && i1 < i0));
+        v = second ? v1 : v0;
+        idx = second ? i1 : i0;
+        __syncthreads();
+    }
+};
+
 // Condensed QP, lane by row in registers: hrow <- row `lane` of 2 sum_i Su_i^T W Su_i (WITHOUT the 2 w_force of the diagonal),
 // grow <- entry `lane` of g = 2 sum_i Su_i^T W (sc_i - ref_i).  Su: [12][ld] scratch in shared memory.  Unknown 3 (NFL i + r) + c =
 // component c of free_leg[r] at stage i; a free_leg entry that is a swing leg is a phantom (no dynamics: its row is zero).
-template <int NFL>
+template <int NFL, int NW = 1>
 __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long prob, int lane, const int (&kind_leg)[4], const int (&free_leg)[4],
                                              double *Su, double (&hrow)[15 * NFL], double &grow) {
     constexpr int n = 15 * NFL, ld = mpcr_even(n);
     const long long N = prm.N;
     const int row = lane < n ? lane : n - 1;
     // ---- condensed QP: H = 2 sum_i Su_i^T W Su_i + 2 R,  g = 2 sum_i Su_i^T W (sc_i - ref_i), lane by row in registers ----
-    for (int e = lane; e < 12 * ld; e += 32) Su[e] = 0.0;
+    for (int e = lane; e < 12 * ld; e += 32 * NW) Su[e] = 0.0;
     grow = 0.0;
 #pragma unroll
     for (int j = 0; j < n; ++j) hrow[j] = 0.0;
@@ -160,7 +219,7 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
     for (int k = 0; k < 12; ++k) sc[k] = prm.x[k * N + prob];
 #pragma unroll
     for (int k = 0; k < 12; ++k) pf[k] = prm.p[k * N + prob];
-    __syncwarp();
+    MpcGroup<NW>::sync();
 #pragma unroll 1
     for (int i = 0; i < MPC_NH; ++i) {
         double th[3];
@@ -177,7 +236,7 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
 #pragma unroll
             for (int a = 0; a < 3; ++a) Su[(3 + a) * ld + c] += prm.dt * Su[(9 + a) * ld + c];
         }
-        __syncwarp();
+        MpcGroup<NW>::sync();
         // Su[:, 3 NFL i + 3 r + c] += dt B: rows 6..8 = Ihat^-1 skew(R p_l), rows 9..11 = I / m;  Ihat^-1 = R diag(1/I) R^T
         if (lane < 3 * NFL) {
             const int c = lane % 3;
@@ -216,7 +275,7 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
             for (int a = 0; a < 3; ++a) sc[3 + a] += prm.dt * sc[9 + a];
             sc[11] += prm.dt * prm.gravity;
         }
-        __syncwarp();
+        MpcGroup<NW>::sync();
         // row `row` of Su_i^T W Su_i: columns beyond 3 NFL (i + 1) of Su are still zero
         double sa[12], gacc = 0.0;
 #pragma unroll
@@ -236,7 +295,7 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
                 hrow[b] = fma(2.0, acc, hrow[b]);
             }
         }
-        __syncwarp();
+        MpcGroup<NW>::sync();
     }
 }
 

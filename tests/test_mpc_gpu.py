@@ -216,3 +216,37 @@ def test_dual_active_set_warm_start_and_solver_agreement():
         assert np.abs(u - want).max() < 1e-8 * max(1.0, np.abs(want).max()), k
         viol, stat = mpc.kkt_certificate(u, H, g, A, b, pinned)
         assert viol < 1e-7 and stat < 1e-8, (k, viol, stat)
+
+
+def test_dual_active_set_with_two_warps_covers_three_and_four_stance_legs():
+    """Orders 45 and 60 (three and four legs out of swing) run the same dual active-set method with two warps per problem
+    (kf_mpc_gi2_kernel); a mixed batch exercises every instantiation, the shared-memory interior point (kf_mpc.cuh) is the yardstick,
+    and a standing batch (all four legs in stance) carries a warm start from one solve to the next."""
+    from optistate_b200.mpc import ST_WARM, WarmStart
+
+    n = 512
+    x, ref, p, c = mpc_cases.batch(n, seed=21)
+    gi, st = mpc_forces(x, ref, p, c)
+    ipm, st_ip = mpc_forces(x, ref, p, c, solver="interior_point")
+    scale = float(ipm.abs().max())
+    assert not (st & 7).any() and not (st_ip & 7).any()
+    assert float((gi - ipm).abs().max()) < 1e-8 * scale
+    four = np.ones((4, n))
+    stand, s0 = mpc_forces(x, ref, p, four)
+    stand_ip, _ = mpc_forces(x, ref, p, four, solver="interior_point")
+    assert not (s0 & 7).any() and float((stand - stand_ip).abs().max()) < 1e-8 * float(stand_ip.abs().max())
+    F = stand.cpu().numpy()
+    for k in range(0, n, 41):
+        H, g, _ = mpc.build_qp(x[:, k], ref[:, :, k].T, p[:, k])
+        A, b, pinned = mpc.constraints(four[:, k])
+        want = mpc.solve_ldp(H, g, A, b, pinned)
+        u = F[:, :, k].reshape(-1)
+        assert np.abs(u - want).max() < 1e-8 * max(1.0, np.abs(want).max()), k
+        viol, stat = mpc.kkt_certificate(u, H, g, A, b, pinned)
+        assert viol < 1e-7 and stat < 1e-8, (k, viol, stat)
+    warm = WarmStart(n)
+    mpc_forces(x, ref, p, four, warm=warm)
+    again, s1 = mpc_forces(x, ref, p, four, warm=warm)
+    constrained = (warm.active[0] & 0xFFFFF) != 0
+    assert float((again - stand).abs().max()) < 1e-9 * float(stand.abs().max()) and bool(((s1 & ST_WARM) != 0)[constrained].all())
+    assert int((s1 >> 8)[constrained].max()) == 0

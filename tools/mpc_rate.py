@@ -1,4 +1,4 @@
-"""Developer helper (GPU box): QPs/s of the batched force MPC.  usage: python tools/mpc_rate.py [n_problems] [trot]"""
+"""Developer helper (GPU box): QPs/s of the batched force MPC.  usage: python tools/mpc_rate.py [n_problems] [trot | stand | three]"""
 import os
 import sys
 
@@ -15,6 +15,9 @@ x, ref, p, c = x.repeat(1, rep), ref.repeat(1, 1, rep), p.repeat(1, rep), c.repe
 if len(sys.argv) > 2 and sys.argv[2] == "trot":  # the gait of the recordings: diagonal leg pairs alternate
     c = torch.where((torch.arange(c.shape[1], device=c.device) % 2 == 0)[None, :], torch.tensor([1.0, 0, 0, 1], device=c.device, dtype=c.dtype)[:, None],
                     torch.tensor([0, 1.0, 1, 0], device=c.device, dtype=c.dtype)[:, None]).contiguous()
+if len(sys.argv) > 2 and sys.argv[2] in ("stand", "three"):  # all four legs in stance / three (a walk)
+    pat = [1.0, 1, 1, 1] if sys.argv[2] == "stand" else [1.0, 1, 0, 1]
+    c = torch.tensor(pat, device=c.device, dtype=c.dtype)[:, None].repeat(1, c.shape[1]).contiguous()
 best = 1e9
 for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
