@@ -686,8 +686,11 @@ def secondary_figures(a, torch, d, dev, dtype, st):
         trot = torch.where((torch.arange(1 << 15, device=dev) % 2 == 0)[None, :], torch.tensor([1.0, 0, 0, 1], device=dev, dtype=torch.float64)[:, None],
                            torch.tensor([0, 1.0, 1, 0], device=dev, dtype=torch.float64)[:, None]).contiguous()
         tqt = once(lambda: mpc_forces(qp[0], qp[1], qp[2], trot))
+        stand = torch.ones((4, 1 << 15), dtype=torch.float64, device=dev)
+        tqs = once(lambda: mpc_forces(qp[0], qp[1], qp[2], stand))
         sec["force_mpc_qps_per_s"] = (1 << 15) / tq
         sec["force_mpc_trot_qps_per_s"] = (1 << 15) / tqt
+        sec["force_mpc_standing_qps_per_s"] = (1 << 15) / tqs
         # the closed loop the shipped driver runs (estimate_state_mpc: QP -> predict_mpc -> update, per step), 65,536 trajectories
         nc, tc = 1 << 16, 20
         rep = nc // min(S, nc)

@@ -493,7 +493,7 @@ __device__ __forceinline__ void mpc_solve_rows(const MpcParams &prm, long long p
                     for (int c = 0; c < 3; ++c) dv[3 * lane + c] -= att[c];
                 }
                 __syncwarp();
-                const double x = M.solve(dv[row], Ls, lane);
+                const double x = M.solve(lane < n ? dv[lane] : 0.0, Ls, lane);  // (surplus lanes carry a dummy entry)
                 if (lane < n) dv[lane] = x;
                 __syncwarp();
                 if (my_act) {
@@ -542,7 +542,7 @@ __device__ __forceinline__ void mpc_solve_rows(const MpcParams &prm, long long p
                 for (int c = 0; c < 3; ++c) dv[3 * lane + c] += att[c];
             }
             __syncwarp();
-            const double x = M.solve(dv[row], Ls, lane);
+            const double x = M.solve(lane < n ? dv[lane] : 0.0, Ls, lane);  // (surplus lanes carry a dummy entry)
             if (lane < n) dv[lane] = x;
             __syncwarp();
             double moved = 0.0;

@@ -250,3 +250,33 @@ def test_dual_active_set_with_two_warps_covers_three_and_four_stance_legs():
     constrained = (warm.active[0] & 0xFFFFF) != 0
     assert float((again - stand).abs().max()) < 1e-9 * float(stand.abs().max()) and bool(((s1 & ST_WARM) != 0)[constrained].all())
     assert int((s1 >> 8)[constrained].max()) == 0
+
+
+def test_batched_closed_loop_with_dense_noise_custom_p0_and_dt():
+    """Non-default arguments of estimate_state_mpc_batch: a dense Q (joint filter step, like the class), a per-call P0, another dt -
+    the model constants reach the MPC AND the filter - against the drop-in class driven step by step."""
+    from optistate_b200.mpc import estimate_state_mpc_batch
+    from optistate_b200.synth import make_streams
+
+    T, N = 5, 2
+    st = make_streams(range(20, 20 + N), T)
+    rng = np.random.default_rng(8)
+    ref = np.zeros((T, 5, 12, N))
+    ref[:, :, 5, :] = 0.28
+    m = 0.01 * rng.standard_normal((12, 12))
+    Q = np.diag(np.full(12, 0.01)) + m @ m.T                       # dense, symmetric positive definite
+    R = np.diag(np.linspace(0.005, 0.02, 10))
+    P0 = np.diag(np.linspace(0.01, 0.03, 12))
+    dt = 0.02
+    xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref, P0=P0, Q=Q, R=R, dt=dt)
+    torch.cuda.synchronize()
+    assert not (mst & 7).any() and int((fst & 2).max()) == 0
+    for n in range(N):
+        kf = Kalman_Filter()
+        kf.x = kf.x.copy()
+        kf.Q, kf.R, kf.P, kf.dt = Q.copy(), R.copy(), P0.copy(), dt
+        for t in range(T):
+            x = kf.estimate_state_mpc(st["imu"][t, :, n].reshape(6, 1), st["p"][t, :, n].reshape(12, 1).copy(), st["dp"][t, :, n].reshape(12, 1),
+                                      ref[t, :, :, n].T, st["contact"][t, :, n].reshape(4, 1))
+            assert np.abs(kf.f[:, 0] - fs[t, :, n].cpu().numpy()).max() < 1e-6 * max(1.0, np.abs(kf.f[:, 0]).max()), (n, t)
+            assert np.abs(x.reshape(12) - xs[t, :, n].cpu().numpy()).max() < 1e-7, (n, t)
