@@ -83,7 +83,8 @@ enum {
  *   diagonal P0 - every cross-group entry of P stays an exact zero in the reference as well, and the SEQUENTIAL kernels drop
  *   the multiplications by those zeros (30 packed scalars instead of 78; bit-identical results).  Diagonal P0 kinds select
  *   this automatically; P0_DECOUPLED lets the caller vouch for a dense P0; FULL_COVARIANCE turns it off (tests, comparison). */
-enum { OPTI_KF_FLAG_P0_DECOUPLED = 1, OPTI_KF_FLAG_FULL_COVARIANCE = 2 };
+enum { OPTI_KF_FLAG_P0_DECOUPLED = 1, OPTI_KF_FLAG_FULL_COVARIANCE = 2,
+       OPTI_KF_FLAG_SCALAR_FP32 = 4 /* FP32: one trajectory per thread even where the packed two-per-thread kernel (FFMA2) applies */ };
 
 /* status[i] bits */
 enum {
@@ -261,13 +262,16 @@ typedef struct OptiKfMpcDesc {
      * neither: the active set (one word per stage: bit 5 leg + row, bits 24..27 legs out of swing, bit 31 valid; zeroed
      * memory = no warm start) and the multipliers of its rows.  A set that verifies (primal and dual feasibility of the
      * equality-constrained solve, the same test that ends the cold path) skips the interior-point phase; one that does
-     * not, or a changed contact pattern, falls back to it.  Used for max_free_legs <= 2, ignored otherwise.            */
+     * not, or a changed contact pattern, falls back to it.  (The shared-memory interior point for three and four legs out of
+     * swing ignores it.)                                                                                              */
     uint32_t *warm_set;            /* [5][N]                                                                           */
     void *warm_mult;               /* [5][4][5][N] doubles                                                              */
     int32_t warm_rounds;           /* active-set correction rounds a warm start may take before the interior point runs
                                       (0 = default)                                                                    */
-    int32_t solver;                /* max_free_legs <= 2: 0 = dual active set, interior point for what it gives up on (default);
-                                      1 = interior point only.  A warm start implies 1.                                */
+    int32_t solver;                /* 0 = dual active set, interior point for what it gives up on (default); 1 = interior point only */
+    int32_t max_changes;           /* dual active set: constraints entered + dropped before a problem is handed to the interior
+                                      point (0 = default 400) - a time budget for real-time callers                     */
+    int32_t reserved0;
     double dt, mass, inertia[3], gravity;
     double mu, fz_max;             /* 0.6, 150 (force_controller.py:149-151)                                          */
     double w_state[12], w_force;   /* diag Q = P (kalman_filter.py:64,70) and the R value (:66)                        */

@@ -134,7 +134,7 @@ def kf_batch(
     algo: str = "auto", cov_model: str = "predict", q_kind=None, r_kind=None, p0_kind=None,
     dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
     gravity: float = INITIAL_PARAMS.GRAVITY, device=None, out: Optional[Dict[str, torch.Tensor]] = None,
-    summary_peers=None, p0_is_symmetric: Optional[bool] = None, structure: str = "auto",
+    summary_peers=None, p0_is_symmetric: Optional[bool] = None, structure: str = "auto", packed: bool = True,
 ) -> KfBatchResult:
     """Runs the Kalman filter over N trajectories x T steps on the current CUDA device.
 
@@ -153,6 +153,7 @@ def kf_batch(
     a dense P0 whose cross-group entries are all zero - checked here) the cross-group entries of P are exact zeros at every
     step, in the reference too, and are neither stored nor multiplied (bit-identical results, less than half the
     arithmetic).  "full" keeps all 78 packed entries regardless (tests, comparison).
+    packed: FP32 only - False keeps one trajectory per thread where the packed two-per-thread kernel (FFMA2) would be chosen.
     summary_peers: an optistate_b200.peer.PeerSummary - the summary is then written into this rank's columns of the
     job-wide [52, n_total] array on EVERY GPU of the box by the filter kernel itself (fused all-gather over NVLink peer
     stores); `result.summary` is the local column block, `summary_peers.tensor` the gathered array once
@@ -191,6 +192,8 @@ def kf_batch(
     if structure not in ("auto", "full"):
         raise ValueError("structure must be 'auto' or 'full'")
     flags = nv.FLAG_FULL_COVARIANCE if structure == "full" else 0
+    if not packed:
+        flags |= nv.FLAG_SCALAR_FP32
     if P0 is not None:
         tensors["P0"], pk = _noise(P0, 12, N, "P0", dtype, device, p0_kind)
         if pk in (nv.MAT_DENSE, nv.MAT_DENSE_PER):

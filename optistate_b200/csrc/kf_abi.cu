@@ -38,7 +38,7 @@ int validate(const OptiKfDesc *d) {
     if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     if (d->summary_ld < 0 || (d->summary_ld > 0 && d->summary_ld < d->n_traj)) return OPTI_KF_E_SHAPE;
     if (d->n_summary_peers < 0 || d->n_summary_peers > OPTI_KF_MAX_PEERS) return OPTI_KF_E_SHAPE;
-    if (d->flags & ~(OPTI_KF_FLAG_P0_DECOUPLED | OPTI_KF_FLAG_FULL_COVARIANCE)) return OPTI_KF_E_SHAPE;
+    if (d->flags & ~(OPTI_KF_FLAG_P0_DECOUPLED | OPTI_KF_FLAG_FULL_COVARIANCE | OPTI_KF_FLAG_SCALAR_FP32)) return OPTI_KF_E_SHAPE;
     for (int k = 0; k < d->n_summary_peers; ++k)
         if (d->summary && !d->summary_peers[k]) return OPTI_KF_E_NULL;
     return OPTI_KF_OK;
@@ -123,11 +123,10 @@ inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7
 // FP32 only: two trajectories per thread on the packed FFMA2 path need even counts, 64-stream tiles and 8-byte
 // aligned per-trajectory arrays (every [C][N] row then starts on a float2 boundary).  Measured on B200 (1.2 M
 // trajectories x 200 steps): packed 1.57e10 vs one-trajectory 1.37e10 steps/s without the summary, 1.31e10 vs 1.07e10
-// with it.  OPTISTATE_KF_PACKED=0 forces the one-trajectory kernel (used by the tests to compare the two).
+// with it.  OPTI_KF_FLAG_SCALAR_FP32 asks for the one-trajectory kernel (the tests compare the two).
 bool packed_pair_ok(const OptiKfDesc *d) {
     if (d->dtype != OPTI_KF_F32) return false;
-    const char *force = std::getenv("OPTISTATE_KF_PACKED");
-    if (force && force[0] == '0') return false;
+    if (d->flags & OPTI_KF_FLAG_SCALAR_FP32) return false;
     if (d->n_traj % 2 != 0 || d->n_streams % 64 != 0 || d->stream_offset % 64 != 0) return false;
     const void *ptrs[] = {d->x0, d->P0, d->Q, d->R, d->x_steps, d->x_model_steps, d->p_world_steps, d->z_steps, d->p_trace_steps,
                           d->k_gain_steps, d->nis_steps, d->P_ckpt, d->x_final, d->P_final, d->summary};
@@ -501,6 +500,7 @@ int optistate_kf_mpc_forces(const OptiKfMpcDesc *d, void *cuda_stream) {
     p.warm_rounds = d->warm_rounds > 0 ? d->warm_rounds : 0;
     if (d->solver != 0 && d->solver != 1) return OPTI_KF_E_SHAPE;
     p.solver = d->solver;
+    p.max_changes = d->max_changes > 0 ? d->max_changes : 0;
     p.dt = d->dt; p.inv_mass = 1.0 / d->mass; p.gravity = d->gravity; p.mu = d->mu; p.fz_max = d->fz_max; p.w_force = d->w_force;
     for (int k = 0; k < 3; ++k) p.inv_inertia[k] = 1.0 / d->inertia[k];
     for (int k = 0; k < 12; ++k) p.w_state[k] = d->w_state[k];

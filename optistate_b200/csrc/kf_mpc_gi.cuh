@@ -144,6 +144,7 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
     int bj = 0, myid = -1;
     int it = 0;
     uint32_t status = 0u;
+    const int max_it = prm.max_changes > 0 ? prm.max_changes : MPCG_MAX_IT;
     const double feas_tol = 1e-9 * prm.fz_max;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double *gr = Ginv + row * ldg;  // this lane's row of H^-1
@@ -368,7 +369,7 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
             uj = is_slot() ? fma(-t, rj, uj) : 0.0;
             up += t;
             ++it;
-            if (it > MPCG_MAX_IT) { ok = false; break; }
+            if (it > max_it) { ok = false; break; }
             if (!dep && t2 <= t1) {  // full step: p enters
                 const Mask freeslots = ~valid & ((Mask(1) << SLOTS) - Mask(1));
                 if (!freeslots) { ok = false; break; }

@@ -16,6 +16,7 @@ struct MpcParams {
     uint32_t *warm_set;                         // [NH][N] optional, in/out: active set of the previous / this solve (kf_mpc_rows.cuh)
     int only_flagged;                           // interior-point kernel: solve only the problems whose status is MPC_ST_GIVEN_UP
     int solver;                                 // 0 auto (dual active set, interior point behind it), 1 interior point
+    int max_changes;                            // dual active set: iteration cap (0 = MPCG_MAX_IT)
     int warm_rounds;                            // polish rounds granted to a warm start
     double *warm_mult;                          // [NH*4*5][N] with warm_set: multipliers of the active rows
     double dt, inv_mass, inv_inertia[3], gravity, mu, fz_max, w_state[12], w_force;

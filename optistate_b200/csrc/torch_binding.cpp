@@ -363,6 +363,8 @@ int kf_mpc_forces(int64_t n, int64_t max_free_legs, const std::map<std::string, 
     }
     auto sv = consts.find("solver");
     d.solver = sv == consts.end() ? 0 : (int32_t)sv->second;
+    auto mc = consts.find("max_changes");
+    d.max_changes = mc == consts.end() ? 0 : (int32_t)mc->second;
     d.dt = consts.at("dt"); d.mass = consts.at("mass"); d.gravity = consts.at("gravity");
     d.inertia[0] = consts.at("inertia0"); d.inertia[1] = consts.at("inertia1"); d.inertia[2] = consts.at("inertia2");
     d.mu = consts.at("mu"); d.fz_max = consts.at("fz_max"); d.w_force = consts.at("w_force");

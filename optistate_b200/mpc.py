@@ -28,15 +28,17 @@ def _dev64(a, device):
 
 def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, mass: float = INITIAL_PARAMS.ROBOT_MASS, inertia=None,
                gravity: float = INITIAL_PARAMS.GRAVITY, mu: float = MU, fz_max: float = FZ_MAX, w_state=W_STATE, w_force: float = W_FORCE,
-               max_free_legs=None, device=None, warm=None, solver: str = "auto"):
+               max_free_legs=None, device=None, warm=None, solver: str = "auto", max_changes: int = 0):
     """Solves N force MPC problems.
 
     x [12, N] current states; body_ref [5, 12, N] reference states of the horizon; p [12, N] body-frame feet;
     contact [4, N] (0 swing, 1 stance).  max_free_legs: bound on the legs out of swing in any problem (None = taken from
     `contact`, which costs one small reduction and a host sync; it sizes the kernel's shared memory).
-    solver: "auto" - for at most two legs out of swing the dual active-set kernel (csrc/kf_mpc_gi.cuh), with the interior-point
-    kernel behind it for problems it gives up on; "interior_point" - the interior-point kernel only (what three and four legs out
-    of swing always get).
+    solver: "auto" - the dual active-set kernels (csrc/kf_mpc_gi.cuh: one warp per problem for at most two legs out of swing, two
+    warps for three and four), with the interior-point kernels behind them for problems they give up on; "interior_point" - the
+    interior-point kernels only.
+    max_changes: cap on the constraints the dual active-set method may enter + drop per problem before it hands the problem to the
+    interior point (0 = the kernel's default, 400).
     warm: a `WarmStart` (in / out) carrying the active set and multipliers from one solve to the next one of the same
     problems (closed loops); a set that no longer verifies falls back to the cold path inside the kernel.
     Returns (forces [5, 12, N] - stage 0 is what predict_mpc applies -, status [N]: ST_* bits | interior-point iterations << 8).
@@ -56,6 +58,7 @@ def mpc_forces(x, body_ref, p, contact, *, dt: float = INITIAL_PARAMS.DT_mpc, ma
     if solver not in ("auto", "interior_point"):
         raise ValueError("solver must be 'auto' or 'interior_point'")
     consts["solver"] = 1.0 if solver == "interior_point" else 0.0
+    consts["max_changes"] = float(max_changes)
     tensors = dict(x=x_t, body_ref=b_t, p=p_t, contact=c_t, forces=forces, status=status)
     if warm is not None:
         if warm.n != n or warm.active.device != device:

@@ -47,7 +47,7 @@ def test_mpc_descriptor_validation():
     class Desc(ctypes.Structure):
         _fields_ = [("struct_size", ctypes.c_uint32), ("abi_version", ctypes.c_uint32), ("dtype", ctypes.c_int32), ("max_free_legs", ctypes.c_int32),
                     ("n_problems", ctypes.c_int64), ("x", P), ("body_ref", P), ("p", P), ("contact", P), ("forces", P), ("status", P),
-                    ("warm_set", P), ("warm_mult", P), ("warm_rounds", ctypes.c_int32), ("solver", ctypes.c_int32), ("dt", D), ("mass", D), ("inertia", D * 3), ("gravity", D), ("mu", D), ("fz_max", D), ("w_state", D * 12), ("w_force", D)]
+                    ("warm_set", P), ("warm_mult", P), ("warm_rounds", ctypes.c_int32), ("solver", ctypes.c_int32), ("max_changes", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("dt", D), ("mass", D), ("inertia", D * 3), ("gravity", D), ("mu", D), ("fz_max", D), ("w_state", D * 12), ("w_force", D)]
 
     d = Desc(struct_size=ctypes.sizeof(Desc), abi_version=lib.optistate_kf_abi_version(), dtype=0, n_problems=4, dt=0.01, mass=8.8,
              gravity=-9.81, mu=0.6, fz_max=150.0, w_force=1e-6)

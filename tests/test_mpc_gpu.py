@@ -280,3 +280,17 @@ def test_batched_closed_loop_with_dense_noise_custom_p0_and_dt():
                                       ref[t, :, :, n].T, st["contact"][t, :, n].reshape(4, 1))
             assert np.abs(kf.f[:, 0] - fs[t, :, n].cpu().numpy()).max() < 1e-6 * max(1.0, np.abs(kf.f[:, 0]).max()), (n, t)
             assert np.abs(x.reshape(12) - xs[t, :, n].cpu().numpy()).max() < 1e-7, (n, t)
+
+
+def test_problems_the_dual_active_set_gives_up_on_are_solved_by_the_interior_point():
+    """The hand-over path: with a budget of three constraint changes most saturated problems are flagged by the dual active-set
+    kernel and solved by the interior-point kernel in the second launch - same forces as without the budget, no flag left."""
+    n = 256
+    x, ref, p, c = mpc_cases.batch(n, seed=13)
+    for contact in (np.where((np.arange(n) % 2 == 0)[None, :], np.array([1.0, 0, 0, 1])[:, None], np.array([0, 1.0, 1, 0])[:, None]), c):
+        full, st = mpc_forces(x, ref, p, contact)
+        capped, st_c = mpc_forces(x, ref, p, contact, max_changes=3)
+        assert not (st & 7).any() and not (st_c & (7 | 16)).any()
+        took_ipm = ((st >> 8) > 3)                       # these needed more than the budget: the second launch solved them
+        assert int(took_ipm.sum()) > n // 8
+        assert float((capped - full).abs().max()) < 1e-8 * float(full.abs().max())

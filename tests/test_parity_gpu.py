@@ -314,7 +314,7 @@ def test_streamed_tma_kernel_matches_oracle_and_direct_kernel(dtype, tol):
     assert flags[130] and flags.sum() // 4 == 1 + (1 if 130 + S < N else 0)
 
 
-def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
+def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle():
     """FP32 with an even trajectory count and 64-stream tiles runs two trajectories per thread on FFMA2/FADD2/FMUL2
     (the F2 instantiation).  It must agree with the one-trajectory-per-thread FP32 kernel to FP32 rounding and with
     the FP64 oracle within the stated FP32 tolerance, including ragged last blocks and the status words."""
@@ -328,11 +328,8 @@ def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
     x0 = cases.START[:, None] + 0.01 * rng.standard_normal((12, N))
     outs = ("x_steps", "p_trace", "k_gain", "nis", "final", "summary", "p_world_steps", "x_model_steps")
     kw = dict(Q=q, R=r, x0=x0, n_traj=N, dtype=torch.float32, outputs=outs, truth=st["truth"], nominal=0.5 * st["truth"], stream_offset=64)
-    monkeypatch.setenv("OPTISTATE_KF_PACKED", "1")
     packed = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
-    monkeypatch.setenv("OPTISTATE_KF_PACKED", "0")
-    scalar = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
-    monkeypatch.delenv("OPTISTATE_KF_PACKED")
+    scalar = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], packed=False, **kw)
     idx = ((np.arange(N) + 64) % S).astype(np.int32)
     ref = c_oracle.run(st, N, Q=q, R=r, x0=x0, stream_index=idx, want=("x_steps", "p_trace_steps", "k_gain_steps", "P_final"))
     scale = np.abs(ref["x_steps"]).max(axis=(0, 2))
@@ -349,7 +346,7 @@ def test_packed_fp32_pair_kernel_matches_scalar_fp32_and_oracle(monkeypatch):
     assert torch.equal(packed.status, scalar.status) and int((packed.status & 4).sum()) // 4 == int((idx == 70).sum())
 
 
-def test_full_size_config3_properties(monkeypatch):
+def test_full_size_config3_properties():
     """BASELINE config 3 at full size (1,048,576 trajectories x 1,000 steps, FP32 Monte-Carlo noise sweep over 1,024 shared
     streams), checked through size-independent properties: nominal members reproduce the nominal run (RMS deviation 0),
     identical (stream, noise) pairs give identical summaries wherever they sit in the batch, no status flags, and a sample
@@ -364,7 +361,6 @@ def test_full_size_config3_properties(monkeypatch):
     r[:, -S:] = r[:, S:2 * S]
     # both passes on the packed two-trajectories-per-thread kernel: the one-trajectory FP32 kernel rounds sin/cos-derived
     # entries differently in the last bit, and "deviation from the nominal member == 0" is a bitwise statement
-    monkeypatch.setenv("OPTISTATE_KF_PACKED", "1")
     nominal = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], dtype=torch.float32, outputs=("x_steps",)).x_steps
     res = kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=q, R=r, n_traj=N, dtype=torch.float32,
                    truth=dev["truth"], nominal=nominal, outputs=("summary",))
@@ -442,7 +438,7 @@ def test_custom_model_constants_and_degenerate_sizes(algo):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_decoupled_group_kernels_are_bit_identical_to_the_full_recursion(dtype, monkeypatch):
+def test_decoupled_group_kernels_are_bit_identical_to_the_full_recursion(dtype):
     """predict()'s F_d couples attitude only with body rate and each position only with its own velocity; with a P0 without
     cross-group entries those entries of P are exact zeros at every step (in the reference goldens too:
     tests/test_oracle.py::test_reference_goldens_have_exact_zero_cross_group_covariance), so the kernels that skip them
@@ -461,15 +457,11 @@ def test_decoupled_group_kernels_are_bit_identical_to_the_full_recursion(dtype, 
     idx = (np.arange(N) % S).astype(np.int32)
     variants = [dict(), dict(stream_index=idx), dict(outputs=("summary",)), dict(outputs=("x_final",))]
     if dtype == torch.float32:
-        variants.append(dict(_packed="0"))  # one FP32 trajectory per thread instead of the packed pair kernel
+        variants.append(dict(packed=False))  # one FP32 trajectory per thread instead of the packed pair kernel
     for v in variants:
-        v = dict(v)
-        if "_packed" in v:
-            monkeypatch.setenv("OPTISTATE_KF_PACKED", v.pop("_packed"))
         kw = dict(base, **v)
         blk = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], **kw)
         full = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], structure="full", **kw)
-        monkeypatch.delenv("OPTISTATE_KF_PACKED", raising=False)
         assert blk.algo == full.algo == "sequential"
         for name, t in full.tensors.items():
             assert torch.equal(blk.tensors[name], t), (name, v, float((blk.tensors[name] - t).abs().max()))

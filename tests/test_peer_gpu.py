@@ -74,11 +74,7 @@ def test_odd_row_stride_takes_the_one_trajectory_fp32_kernel():
     S, T, N = 64, 20, 128
     d, q, r = _inputs(S, T, N, torch.float32)
     kw = dict(Q=q, R=r, n_traj=N, dtype=torch.float32, truth=d["truth"], outputs=("summary",), q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER)
-    os.environ["OPTISTATE_KF_PACKED"] = "0"
-    try:
-        plain = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], **kw)
-    finally:
-        del os.environ["OPTISTATE_KF_PACKED"]
+    plain = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], packed=False, **kw)
     peers = LoopbackPeers(2 * N + 1, N, N, torch.float32, n_peers=1)
     fused = kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], summary_peers=peers, **kw)
     torch.cuda.synchronize()
