@@ -83,7 +83,7 @@ template <int NFL, int NW>
 __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long prob, double *base, const int (&kind_leg)[4], const int (&free_leg)[4]) {
     using G = MpcGroup<NW>;
     constexpr int n = 15 * NFL, nb = 5 * NFL, ldg = n | 1, GT = G::threads, SLOTS = mpcg_slots(NFL), LDP = SLOTS + 1;
-    static_assert(n <= GT && SLOTS <= GT && 12 * mpcr_even(n) <= n * ldg && GT == mpcg_group(NFL), "layout");
+    static_assert(n <= GT && SLOTS <= GT && mpc_condense_scratch(NFL) <= n * ldg && GT == mpcg_group(NFL), "layout");
     const long long N = prm.N;
     const int lane = G::tid();  // index in the group: row / slot / constraint block owned by this thread
     double *Ginv = base, *Su = base, *P = Ginv + mpcr_even(n * ldg), *xs = P + SLOTS * LDP, *g = xs + GT, *strip = g + GT;

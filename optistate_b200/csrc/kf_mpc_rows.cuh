@@ -200,17 +200,31 @@ struct MpcGroup<2> {  // one problem per 64-thread block
     }
 };
 
-// Condensed QP, lane by row in registers: hrow <- row `lane` of 2 sum_i Su_i^T W Su_i (WITHOUT the 2 w_force of the diagonal),
-// grow <- entry `lane` of g = 2 sum_i Su_i^T W (sc_i - ref_i).  Su: [12][ld] scratch in shared memory.  Unknown 3 (NFL i + r) + c =
-// component c of free_leg[r] at stage i; a free_leg entry that is a swing leg is a phantom (no dynamics: its row is zero).
+// Condensed QP, thread by row in registers: hrow <- row `lane` of 2 sum_i Su_i^T W Su_i (WITHOUT the 2 w_force of the diagonal),
+// grow <- entry `lane` of g = 2 sum_i Su_i^T W (sc_i - ref_i).  `lane` is the thread's index in its group (MpcGroup<NW>).
+// Unknown 3 (NFL i + r) + c = component c of free_leg[r] at stage i; a free_leg entry that is a swing leg is a phantom (no
+// dynamics: its row and column are zero).
+// scratch: shared memory, mpc_condense_scratch(NFL) doubles: the sensitivities Su [12][ld] of the stage state to the forces, the five
+// rotation matrices of the horizon and its 60 reference values.
+//   * the rotations (three sin / cos pairs each) are evaluated ONCE, stage i by thread i, instead of by every thread in every
+//     stage; the reference states are fetched once, coalesced, instead of one dependent global load per use;
+//   * rows 3..5 and 9..11 of Su (position and velocity sensitivities) are known in closed form - a force component c of stage j
+//     changes velocity c by dt / m from stage j on and position c by (i - j) dt^2 / m at stage i, nothing else - so their part of
+//     the Gram matrix, sum_i over the common stages of w_pos (i - j)(i - j') (dt^2 / m)^2 + w_vel (dt / m)^2 for equal components,
+//     is added once at the end, and the per-stage accumulation runs over the six attitude / body-rate rows only (pairs of columns
+//     per 16-byte load): half the FMAs and a third of the shared-memory loads of the straightforward form.
+__host__ __device__ constexpr int mpc_condense_scratch(int nfl) { return 12 * mpcr_even(15 * nfl) + 48 + 64; }
+
 template <int NFL, int NW = 1>
 __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long prob, int lane, const int (&kind_leg)[4], const int (&free_leg)[4],
-                                             double *Su, double (&hrow)[15 * NFL], double &grow) {
-    constexpr int n = 15 * NFL, ld = mpcr_even(n);
+                                             double *scratch, double (&hrow)[15 * NFL], double &grow) {
+    using G = MpcGroup<NW>;
+    constexpr int n = 15 * NFL, ld = mpcr_even(n), GT = G::threads;
     const long long N = prm.N;
     const int row = lane < n ? lane : n - 1;
-    // ---- condensed QP: H = 2 sum_i Su_i^T W Su_i + 2 R,  g = 2 sum_i Su_i^T W (sc_i - ref_i), lane by row in registers ----
-    for (int e = lane; e < 12 * ld; e += 32 * NW) Su[e] = 0.0;
+    double *Su = scratch, *Rs = scratch + 12 * ld, *bref = Rs + 48;  // Rs [5][9] (padded), bref [5][12]
+    for (int e = lane; e < 12 * ld; e += GT) Su[e] = 0.0;
+    for (int e = lane; e < MPC_NH * 12; e += GT) bref[e] = prm.body_ref[(long long)e * N + prob];
     grow = 0.0;
 #pragma unroll
     for (int j = 0; j < n; ++j) hrow[j] = 0.0;
@@ -219,15 +233,29 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
     for (int k = 0; k < 12; ++k) sc[k] = prm.x[k * N + prob];
 #pragma unroll
     for (int k = 0; k < 12; ++k) pf[k] = prm.p[k * N + prob];
-    MpcGroup<NW>::sync();
+    bool real[NFL];  // leg r of the unknowns carries a force (not a phantom)
+#pragma unroll
+    for (int r = 0; r < NFL; ++r) {
+        real[r] = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q == free_leg[r]) real[r] = kind_leg[q] != 0;
+    }
+    G::sync();
+    if (lane < MPC_NH) {  // linearisation attitude of stage i: the current state for stage 0, body_ref[:, i - 1] after
+        double R[9];
+        if (lane == 0) rot_zyx(sc[0], sc[1], sc[2], R);
+        else rot_zyx(bref[(lane - 1) * 12], bref[(lane - 1) * 12 + 1], bref[(lane - 1) * 12 + 2], R);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rs[9 * lane + k] = R[k];
+    }
+    G::sync();
 #pragma unroll 1
     for (int i = 0; i < MPC_NH; ++i) {
-        double th[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) th[k] = i == 0 ? sc[k] : prm.body_ref[((i - 1) * 12 + k) * N + prob];
         double R[9];
-        rot_zyx(th[0], th[1], th[2], R);
-        // Su <- (I + dt A) Su: rows 0..2 += dt R^T rows 6..8, rows 3..5 += dt rows 9..11
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rs[9 * i + k];
+        // Su <- (I + dt A) Su: rows 0..2 += dt R^T rows 6..8, rows 3..5 += dt rows 9..11 (rows 6..11 unchanged)
         if (lane < n) {
             const int c = lane;
             const double w0 = Su[6 * ld + c], w1 = Su[7 * ld + c], w2 = Su[8 * ld + c];
@@ -236,19 +264,19 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
 #pragma unroll
             for (int a = 0; a < 3; ++a) Su[(3 + a) * ld + c] += prm.dt * Su[(9 + a) * ld + c];
         }
-        MpcGroup<NW>::sync();
+        G::sync();
         // Su[:, 3 NFL i + 3 r + c] += dt B: rows 6..8 = Ihat^-1 skew(R p_l), rows 9..11 = I / m;  Ihat^-1 = R diag(1/I) R^T
         if (lane < 3 * NFL) {
             const int c = lane % 3;
             int l = 0;
+            bool real_leg = false;
 #pragma unroll
             for (int r = 0; r < NFL; ++r)
-                if (r == lane / 3) l = free_leg[r];
+                if (r == lane / 3) { l = free_leg[r]; real_leg = real[r]; }
             double pl[3] = {0.0, 0.0, 0.0};
-            bool real_leg = false;  // a lone stance leg is paired with a phantom (a swing leg): no dynamics, its forces stay zero
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (q == l) { pl[0] = pf[3 * q]; pl[1] = pf[3 * q + 1]; pl[2] = pf[3 * q + 2]; real_leg = kind_leg[q] != 0; }
+                if (q == l) { pl[0] = pf[3 * q]; pl[1] = pf[3 * q + 1]; pl[2] = pf[3 * q + 2]; }
             double pw[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) pw[a] = R[3 * a] * pl[0] + R[3 * a + 1] * pl[1] + R[3 * a + 2] * pl[2];
@@ -275,27 +303,61 @@ __device__ __forceinline__ void mpc_condense(const MpcParams &prm, long long pro
             for (int a = 0; a < 3; ++a) sc[3 + a] += prm.dt * sc[9 + a];
             sc[11] += prm.dt * prm.gravity;
         }
-        MpcGroup<NW>::sync();
-        // row `row` of Su_i^T W Su_i: columns beyond 3 NFL (i + 1) of Su are still zero
-        double sa[12], gacc = 0.0;
+        G::sync();
+        // gradient: all twelve rows of this thread's column; Gram matrix: the attitude (0..2) and body-rate (6..8) rows, columns in pairs
+        double sa[6], gacc = 0.0;
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
             const double s_k = Su[k * ld + row];
-            sa[k] = prm.w_state[k] * s_k;
-            gacc = fma(s_k, prm.w_state[k] * (sc[k] - prm.body_ref[(i * 12 + k) * N + prob]), gacc);
+            if (k < 3) sa[k] = prm.w_state[k] * s_k;
+            if (k >= 6 && k < 9) sa[k - 3] = prm.w_state[k] * s_k;
+            gacc = fma(s_k, prm.w_state[k] * (sc[k] - bref[i * 12 + k]), gacc);
         }
         grow = fma(2.0, gacc, grow);
-        const int ncol = 3 * NFL * (i + 1);
+        const int ncol = 3 * NFL * (i + 1);  // the later columns of Su are still zero
 #pragma unroll
-        for (int b = 0; b < n; ++b) {
-            if (b < ncol) {  // warp-uniform
-                double acc = 0.0;
+        for (int b = 0; b + 1 < n; b += 2) {
+            if (b < ncol) {  // uniform; ncol is even or the odd last column is handled below
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 12; ++k) acc = fma(sa[k], Su[k * ld + b], acc);
-                hrow[b] = fma(2.0, acc, hrow[b]);
+                for (int k = 0; k < 6; ++k) {
+                    const double2 v = *reinterpret_cast<const double2 *>(Su + (k < 3 ? k : k + 3) * ld + b);
+                    a0 = fma(sa[k], v.x, a0);
+                    a1 = fma(sa[k], v.y, a1);
+                }
+                hrow[b] = fma(2.0, a0, hrow[b]);
+                hrow[b + 1] = fma(2.0, a1, hrow[b + 1]);
             }
         }
-        MpcGroup<NW>::sync();
+        if (n & 1) {
+            double a0 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a0 = fma(sa[k], Su[(k < 3 ? k : k + 3) * ld + n - 1], a0);
+            hrow[n - 1] = fma(2.0, a0, hrow[n - 1]);
+        }
+        G::sync();
+    }
+    // closed-form part: position and velocity rows (see the header)
+    {
+        const int jr = row / (3 * NFL), rr = (row / 3) % NFL, cr = row % 3;
+        bool real_row = false;
+#pragma unroll
+        for (int r = 0; r < NFL; ++r)
+            if (r == rr) real_row = real[r];
+        const double d2m = prm.dt * prm.dt * prm.inv_mass, d1m = prm.dt * prm.inv_mass;
+        double wp = 0.0, wv = 0.0;  // 2 w_pos (dt^2 / m)^2 and 2 w_vel (dt / m)^2 of this row's component
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (c == cr) { wp = 2.0 * prm.w_state[3 + c] * d2m * d2m; wv = 2.0 * prm.w_state[9 + c] * d1m * d1m; }
+#pragma unroll
+        for (int b = 0; b < n; ++b) {
+            const int jb = b / (3 * NFL), rb = (b / 3) % NFL, cb = b % 3;  // compile-time after unrolling
+            int s1 = 0, cnt = 0;  // sum over the common stages i >= max(jr, jb) of (i - jr)(i - jb), and their number
+#pragma unroll
+            for (int i = 0; i < MPC_NH; ++i)
+                if (i >= jb && i >= jr) { s1 += (i - jr) * (i - jb); ++cnt; }
+            if (cb == cr && real_row && real[rb]) hrow[b] += wp * (double)s1 + wv * (double)cnt;
+        }
     }
 }
 
@@ -307,7 +369,7 @@ __device__ __forceinline__ void mpc_solve_rows(const MpcParams &prm, long long p
                                                const int (&free_leg)[4]) {
     constexpr int n = 15 * NFL, nb = 5 * NFL, ntri = n * (n + 1) / 2, ld = mpcr_even(n);
     const long long N = prm.N;
-    static_assert(12 * ld <= n * (n | 1), "the sensitivities fit the factor's storage");
+    static_assert(mpc_condense_scratch(NFL) <= n * (n | 1), "the scratch of the condensation fits the factor's storage");
     double *H = base, *Ls = H + mpcr_even(ntri), *Su = Ls, *u = Ls + mpcr_even(n * (n | 1)), *g = u + ld, *rv = g + ld, *dv = rv + ld, *ukeep = dv + ld;
     double *strip = ukeep + ld, *blk = strip + 128;
 
