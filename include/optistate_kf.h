@@ -84,7 +84,9 @@ enum {
  *   the multiplications by those zeros (30 packed scalars instead of 78; bit-identical results).  Diagonal P0 kinds select
  *   this automatically; P0_DECOUPLED lets the caller vouch for a dense P0; FULL_COVARIANCE turns it off (tests, comparison). */
 enum { OPTI_KF_FLAG_P0_DECOUPLED = 1, OPTI_KF_FLAG_FULL_COVARIANCE = 2,
-       OPTI_KF_FLAG_SCALAR_FP32 = 4 /* FP32: one trajectory per thread even where the packed two-per-thread kernel (FFMA2) applies */ };
+       OPTI_KF_FLAG_SCALAR_FP32 = 4, /* FP32: one trajectory per thread even where the packed two-per-thread kernel (FFMA2) applies */
+       OPTI_KF_FLAG_STATUS_ACCUMULATE = 8 /* status[i] |= this call's flags instead of = (one stream per trajectory, no pre-pass):
+                                             lets a caller that steps the filter call by call keep one status word per trajectory */ };
 
 /* status[i] bits */
 enum {
@@ -277,6 +279,38 @@ typedef struct OptiKfMpcDesc {
     double w_state[12], w_force;   /* diag Q = P (kalman_filter.py:64,70) and the R value (:66)                        */
 } OptiKfMpcDesc;
 int optistate_kf_mpc_forces(const OptiKfMpcDesc *desc, void *cuda_stream);
+
+/* ---- the closed loop the reference's conversion driver runs: KF.estimate_state_mpc(imu, p, dp, body_ref, contact) at every
+ * step of every recording (data_conversion_Kalman_to_Training.py:193-201, kalman_filter.py:140-162,176-182).  For N trajectories
+ * over T steps, all on the device and queued on the stream without a host synchronisation: the measurements of all steps in one
+ * pre-pass (they do not depend on the state), then per step the force MPC of every trajectory from its CURRENT estimate
+ * (optistate_kf_mpc_forces, warm-started from the previous step) and one filter step with those forces and the predict_mpc
+ * covariance model (optistate_kf_batch, SEQUENTIAL: diagonal Q / R and a symmetric P0 - callers with dense noise step
+ * optistate_kf_batch(algo = JOINT) themselves).  FP64. ---- */
+typedef struct OptiKfClosedLoopDesc {
+    uint32_t struct_size, abi_version;
+    int32_t dtype;                 /* OPTI_KF_F64 */
+    int32_t max_free_legs;         /* bound on the legs with contact != 0 at any step of any trajectory (1..4; 0 = unknown = 4) */
+    int64_t n_traj, n_steps;
+    const void *imu, *p, *dp, *contact; /* [T][6|12|12|4][N] */
+    const void *body_ref;          /* [T][5][12][N]: horizon reference of every step; the filter's transition uses column 0   */
+    const void *x0; int32_t x0_per_traj;   /* [12] or [12][N] */
+    int32_t p0_kind, q_kind, r_kind;       /* OPTI_KF_MAT_NONE (P0 = Q) / _DIAG / _DIAG_PER; P0 also _DENSE / _DENSE_PER (symmetric) */
+    const void *P0, *Q, *R;
+    void *x_steps;                 /* [T][12][N] posterior state after every step (required)                              */
+    void *forces;                  /* [T][12][N] optional: the stage-0 forces the MPC found and the filter applied         */
+    void *p_world_steps;           /* [T][12][N] optional: feet rotated into the world frame (the driver's feature rows)   */
+    uint32_t *mpc_status;          /* [T][N] optional: OPTI_KF_MPC_ST_* | iterations << 8 of every solve                    */
+    uint32_t *status;              /* [N] optional: OPTI_KF_ST_* accumulated over the steps                                 */
+    void *workspace;               /* device scratch of optistate_kf_closed_loop_workspace_bytes(n_traj, n_steps)          */
+    size_t workspace_bytes;
+    double dt, mass, inertia[3], gravity;
+    double mu, fz_max, w_state[12], w_force;
+    int32_t warm_start;            /* 1: carry the MPC's working set from step to step (default use), 0: cold solves       */
+    int32_t solver, max_changes, reserved0;   /* as in OptiKfMpcDesc */
+} OptiKfClosedLoopDesc;
+size_t optistate_kf_closed_loop_workspace_bytes(int64_t n_traj, int64_t n_steps);
+int optistate_kf_closed_loop(const OptiKfClosedLoopDesc *desc, void *cuda_stream);
 
 /* Runs the filter; dtype taken from the descriptor. */
 int optistate_kf_batch(const OptiKfDesc *desc, void *cuda_stream);

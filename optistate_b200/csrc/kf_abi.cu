@@ -38,7 +38,7 @@ int validate(const OptiKfDesc *d) {
     if (d->stream_index == nullptr && d->stream_offset < 0) return OPTI_KF_E_SHAPE;
     if (d->summary_ld < 0 || (d->summary_ld > 0 && d->summary_ld < d->n_traj)) return OPTI_KF_E_SHAPE;
     if (d->n_summary_peers < 0 || d->n_summary_peers > OPTI_KF_MAX_PEERS) return OPTI_KF_E_SHAPE;
-    if (d->flags & ~(OPTI_KF_FLAG_P0_DECOUPLED | OPTI_KF_FLAG_FULL_COVARIANCE | OPTI_KF_FLAG_SCALAR_FP32)) return OPTI_KF_E_SHAPE;
+    if (d->flags & ~(OPTI_KF_FLAG_P0_DECOUPLED | OPTI_KF_FLAG_FULL_COVARIANCE | OPTI_KF_FLAG_SCALAR_FP32 | OPTI_KF_FLAG_STATUS_ACCUMULATE)) return OPTI_KF_E_SHAPE;
     for (int k = 0; k < d->n_summary_peers; ++k)
         if (d->summary && !d->summary_peers[k]) return OPTI_KF_E_NULL;
     return OPTI_KF_OK;
@@ -159,6 +159,11 @@ int launch(const OptiKfDesc *d, int algo, cudaStream_t stream) {
     if (d->n_traj == 0) return OPTI_KF_OK;
     okf::Params<Real> p = make_params<Real>(d);
     cudaGetLastError();
+    if ((d->flags & OPTI_KF_FLAG_STATUS_ACCUMULATE) && d->status) {
+        // the kernels OR stream_status[stream of i] into what they write: with one stream per trajectory that is the old status
+        if (d->stream_index != nullptr || d->n_streams != d->n_traj || d->stream_offset != 0 || d->phases == OPTI_KF_PHASE_ALL) return OPTI_KF_E_UNSUPPORTED;
+        p.stream_status = d->status;
+    }
     if (algo == OPTI_KF_ALGO_SEQUENTIAL) {
         bool streamed = tma_layout_ok(d);
         if (streamed && d->phases == OPTI_KF_PHASE_ALL) {

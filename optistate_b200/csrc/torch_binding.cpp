@@ -372,6 +372,61 @@ int kf_mpc_forces(int64_t n, int64_t max_free_legs, const std::map<std::string, 
     return optistate_kf_mpc_forces(&d, at::cuda::getCurrentCUDAStream().stream());
 }
 
+// The closed loop of the reference driver (estimate_state_mpc at every step) for N trajectories x T steps: one call, queued on the
+// current stream.  tensors: imu p dp contact body_ref x0 Q R [P0] x_steps workspace [forces p_world_steps mpc_status status]
+int kf_closed_loop(const std::map<std::string, int64_t> &cfg, const std::map<std::string, double> &consts, const std::vector<double> &w_state,
+                   const TensorMap &tensors) {
+    OptiKfClosedLoopDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = OPTI_KF_F64;
+    const int64_t N = cfg.at("n_traj"), T = cfg.at("n_steps");
+    d.n_traj = N; d.n_steps = T;
+    d.max_free_legs = (int32_t)geti(cfg, "max_free_legs", 0);
+    d.x0_per_traj = (int32_t)geti(cfg, "x0_per_traj", 1);
+    d.p0_kind = (int32_t)geti(cfg, "p0_kind", OPTI_KF_MAT_NONE);
+    d.q_kind = (int32_t)geti(cfg, "q_kind", OPTI_KF_MAT_DIAG);
+    d.r_kind = (int32_t)geti(cfg, "r_kind", OPTI_KF_MAT_DIAG);
+    d.warm_start = (int32_t)geti(cfg, "warm_start", 1);
+    d.solver = (int32_t)geti(cfg, "solver", 0);
+    d.max_changes = (int32_t)geti(cfg, "max_changes", 0);
+    auto x = tensors.find("imu");
+    TORCH_CHECK(x != tensors.end() && x->second.is_cuda(), "optistate_b200: 'imu' must be a CUDA tensor (there is no CPU path)");
+    TORCH_CHECK(w_state.size() == 12, "optistate_b200: w_state needs 12 entries");
+    const Checker ck{at::kDouble, x->second.device()};
+    const c10::cuda::CUDAGuard guard(ck.dev);
+    d.imu = ck.get(tensors, "imu", T * 6 * N, true);
+    d.p = ck.get(tensors, "p", T * 12 * N, true);
+    d.dp = ck.get(tensors, "dp", T * 12 * N, true);
+    d.contact = ck.get(tensors, "contact", T * 4 * N, true);
+    d.body_ref = ck.get(tensors, "body_ref", T * OPTI_KF_MPC_HORIZON * 12 * N, true);
+    d.x0 = ck.get(tensors, "x0", d.x0_per_traj ? 12 * N : 12, true);
+    d.Q = ck.get(tensors, "Q", mat_numel(d.q_kind, 12, N), true);
+    d.R = ck.get(tensors, "R", mat_numel(d.r_kind, 10, N), true);
+    if (d.p0_kind != OPTI_KF_MAT_NONE) d.P0 = ck.get(tensors, "P0", mat_numel(d.p0_kind, 12, N), true);
+    d.x_steps = const_cast<void *>(ck.get(tensors, "x_steps", T * 12 * N, true));
+    d.forces = const_cast<void *>(ck.get(tensors, "forces", T * 12 * N, false));
+    d.p_world_steps = const_cast<void *>(ck.get(tensors, "p_world_steps", T * 12 * N, false));
+    for (const char *name : {"mpc_status", "status"}) {
+        auto it = tensors.find(name);
+        if (it == tensors.end()) continue;
+        const at::Tensor &t = it->second;
+        const int64_t want = std::string(name) == "status" ? N : T * N;
+        TORCH_CHECK(t.is_cuda() && t.device() == ck.dev && t.scalar_type() == at::kInt && t.is_contiguous() && t.numel() == want, "optistate_b200: bad '", name, "'");
+        (std::string(name) == "status" ? d.status : d.mpc_status) = reinterpret_cast<uint32_t *>(t.data_ptr<int32_t>());
+    }
+    auto w = tensors.find("workspace");
+    TORCH_CHECK(w != tensors.end() && w->second.is_cuda() && w->second.device() == ck.dev && w->second.is_contiguous(), "optistate_b200: bad 'workspace'");
+    d.workspace = w->second.data_ptr();
+    d.workspace_bytes = (size_t)w->second.numel() * w->second.element_size();
+    d.dt = consts.at("dt"); d.mass = consts.at("mass"); d.gravity = consts.at("gravity");
+    d.inertia[0] = consts.at("inertia0"); d.inertia[1] = consts.at("inertia1"); d.inertia[2] = consts.at("inertia2");
+    d.mu = consts.at("mu"); d.fz_max = consts.at("fz_max"); d.w_force = consts.at("w_force");
+    for (int k = 0; k < 12; ++k) d.w_state[k] = w_state[k];
+    return optistate_kf_closed_loop(&d, at::cuda::getCurrentCUDAStream().stream());
+}
+
 // ---- peer memory (fused summary all-gather) ----
 at::Tensor peer_alloc(int64_t nbytes, int64_t device_index) {
     TORCH_CHECK(nbytes > 0, "optistate_b200: peer_alloc needs a positive size");
@@ -463,6 +518,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_minmax", &kf_minmax);
     m.def("kf_windows", &kf_windows);
     m.def("kf_mpc_forces", &kf_mpc_forces);
+    m.def("kf_closed_loop", &kf_closed_loop);
+    m.def("kf_closed_loop_workspace_bytes", [](int64_t n, int64_t t) { return (int64_t)optistate_kf_closed_loop_workspace_bytes(n, t); });
     m.def("peer_alloc", &peer_alloc);
     m.def("peer_export", &peer_export);
     m.def("peer_open", &peer_open);

@@ -96,7 +96,9 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     imu [T,6,N], p [T,12,N], dp [T,12,N], contact [T,4,N], body_ref [T,5,12,N] (horizon reference of each step; the
     filter's transition uses its first column, as the class does).  x0, P0, Q, R as in kf_batch (P0 None = Q); dense Q / R or a
     non-symmetric P0 run the filter step in its joint form, like the class.  dt, mass, inertia, gravity are the model constants
-    of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs, solver, warm) goes to mpc_forces only.
+    of BOTH the MPC and the filter; `mpc_kw` (mu, fz_max, w_state, w_force, max_free_legs, solver, max_changes; warm = True / False /
+    a WarmStart) goes to the MPC only.  With diagonal noise and a symmetric P0 the whole loop is ONE call of the C ABI
+    (optistate_kf_closed_loop: nothing between the steps goes through Python or synchronises with the host).
     Returns (x_steps [T,12,N], forces [T,12,N] - the applied stage-0 forces -, mpc_status [T,N], filter status [N]) and, with
     return_p_world, the feet rotated into the world frame [T,12,N] (the reference's in-place mutation of p, which its driver
     writes into the GRU feature rows).
@@ -131,8 +133,32 @@ def estimate_state_mpc_batch(imu, p, dp, contact, body_ref, x0=None, P0=None, Q=
     model = dict(dt=dt, mass=mass, inertia=inertia, gravity=gravity)
     if "max_free_legs" not in mpc_kw:
         mpc_kw["max_free_legs"] = max(1, int((contact != 0).sum(dim=1).max())) if T * N > 0 else 4
-    if "warm" not in mpc_kw:  # consecutive QPs of a trajectory differ by one filter step: the working set carries over
-        mpc_kw["warm"] = WarmStart(N, device)
+    warm = mpc_kw.pop("warm", True)  # True: carry the MPC's working set from step to step; False / None: cold solves; or a WarmStart
+    if algo == "sequential" and T * N > 0 and (warm is None or isinstance(warm, bool)) \
+            and set(mpc_kw) <= {"max_free_legs", "mu", "fz_max", "w_state", "w_force", "solver", "max_changes"}:
+        # the whole loop in one call of the C ABI (optistate_kf_closed_loop): no Python, no host synchronisation between the steps
+        ext = nv.ext()
+        I3 = np.diag(INITIAL_PARAMS.INERTIA_ROT) if inertia is None else np.asarray(inertia, float).reshape(3)
+        consts = dict(dt=float(dt), mass=float(mass), inertia0=float(I3[0]), inertia1=float(I3[1]), inertia2=float(I3[2]), gravity=float(gravity),
+                      mu=float(mpc_kw.get("mu", MU)), fz_max=float(mpc_kw.get("fz_max", FZ_MAX)), w_force=float(mpc_kw.get("w_force", W_FORCE)))
+        cfg = dict(n_traj=N, n_steps=T, max_free_legs=int(mpc_kw["max_free_legs"]), x0_per_traj=1, q_kind=q_kind, r_kind=r_kind,
+                   p0_kind=nv.MAT_NONE if Pm is None else p_kind, warm_start=1 if warm is True else 0,
+                   solver=1 if mpc_kw.get("solver", "auto") == "interior_point" else 0, max_changes=int(mpc_kw.get("max_changes", 0)))
+        tensors = dict(imu=imu, p=p, dp=dp, contact=contact, body_ref=body_ref, x0=x.contiguous(), Q=q_t, R=r_t, x_steps=xs, forces=fs,
+                       mpc_status=mst, status=fst,
+                       workspace=torch.empty(int(ext.kf_closed_loop_workspace_bytes(N, T)), dtype=torch.uint8, device=device))
+        if Pm is not None:
+            tensors["P0"] = Pm
+        if return_p_world:
+            tensors["p_world_steps"] = pws
+        with torch.cuda.device(device):
+            nv.check(int(ext.kf_closed_loop(cfg, consts, [float(w) for w in mpc_kw.get("w_state", W_STATE)], tensors)), "optistate_kf_closed_loop")
+        return (xs, fs, mst, fst, pws) if return_p_world else (xs, fs, mst, fst)
+    # dense noise or a non-symmetric P0 (the joint filter step), or a caller-owned WarmStart: stepped from here
+    if mpc_kw.get("warm", None) in (True, None) and "warm" in mpc_kw:
+        del mpc_kw["warm"]
+    if mpc_kw.get("warm", None) is False:
+        mpc_kw["warm"] = None
     for t in range(T):
         forces, st = mpc_forces(x, body_ref[t], p[t], contact[t], **model, **mpc_kw)
         fs[t], mst[t] = forces[0], st

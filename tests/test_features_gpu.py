@@ -95,3 +95,9 @@ def test_example_driver_pipeline_runs_and_is_consistent():
     assert torch.equal(rows[:, :, 0:12], res.x_steps.permute(2, 0, 1))  # the first 12 feature columns are the estimates
     w = windows[torch.isfinite(windows)]
     assert w.min() >= 0.0 and w.max() <= 1.0
+    # the shipped driver's own call (estimate_state_mpc: the force MPC solved from the current estimate at every step)
+    cl, rows_cl, windows_cl = mod.run(n_recordings=8, n_steps=40, seq_len=10, closed_loop=True)
+    assert int(cl.status.max()) == 0 and not (cl.mpc_status & 7).any()
+    assert rows_cl.shape == (8, 40, 60) and windows_cl.shape == (8, 31, 10, 60)
+    assert torch.equal(rows_cl[:, :, 0:12], cl.x_steps.permute(2, 0, 1)) and bool(torch.isfinite(rows_cl).all())
+    assert float(rows_cl[:, :, 18:30].abs().max()) > 1.0   # columns 18..29 hold the forces the MPC found

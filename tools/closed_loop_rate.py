@@ -24,7 +24,7 @@ rounds = int(os.environ.get("WARM_ROUNDS", "0"))
 for _ in range(2):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    kw = {"warm": None} if rounds < 0 else {}  # default: the dual active-set kernel with its warm start; WARM_ROUNDS=-1: cold
+    kw = {"warm": False} if rounds < 0 else {}  # default: the dual active-set kernel with its warm start; WARM_ROUNDS=-1: cold
     xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref, **kw)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0

@@ -1,3 +1,5 @@
-mkdir -p gpurun_out/r2j
-timeout 300 python __graft_entry__.py smoke > gpurun_out/r2j/smoke.txt 2>&1; echo "smoke rc=$?"; tail -6 gpurun_out/r2j/smoke.txt
-timeout 600 python bench.py > gpurun_out/r2j/bench_f64.json 2> gpurun_out/r2j/bench_f64.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/r2j/bench_f64.json
+timeout 600 python -m pytest tests/test_mpc_gpu.py tests/test_reference_driver_gpu.py tests/test_features_gpu.py -m gpu -q -x 2>&1 | tail -8
+timeout 120 python tools/closed_loop_rate.py 65536 20
+timeout 120 python tools/closed_loop_rate.py 1024 200
+timeout 120 python tools/closed_loop_rate.py 64 400
+timeout 300 python examples/driver_pipeline.py 64 4063 --closed-loop 2>&1 | tail -1
