@@ -350,9 +350,13 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
             // r = S^-1 d, z = y - H^-1 N r
             const double rj = is_slot() ? times_sinv(dslot) : 0.0;
             rslot[lane] = rj;
-            const double zn = nGn - G::sum(dj * rj, scr);
+            double zn = 0.0;
+            if constexpr (NW == 2) zn = nGn - G::sum(dj * rj, scr);
             G::sync();
             const double zi = yi - times_hinv_n(rslot);
+            if constexpr (NW == 1) {  // n_p^T z = n^T H^-1 n - d^T r: three entries of z instead of a warp-wide sum
+                zn = fma(np2, __shfl_sync(0xffffffffu, zi, 3 * bp + 2), fma(np1, __shfl_sync(0xffffffffu, zi, 3 * bp + 1), np0 * __shfl_sync(0xffffffffu, zi, 3 * bp)));
+            }
             const bool dep = !(zn > 1e-12 * nGn);  // n_p is (numerically) a combination of the working normals: dual step only
             // step lengths: t1 keeps the multipliers non-negative, t2 makes constraint p hold
             double t1 = (is_slot() && rj > 1e-300) ? uj * rcp2_(rj) : inf;

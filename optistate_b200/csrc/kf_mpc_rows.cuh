@@ -145,12 +145,21 @@ struct MpcRows {
 // kf_mpc_gi.cuh - the two warps of a 64-thread block.  Thread t of the group owns row t / slot t / constraint block t.
 // `scr`: eight doubles of shared memory per problem (only the two-warp form touches it).
 __device__ __forceinline__ void warp_argmin(double &v, int &idx) {  // smallest (value, index); ties to the smaller index; index < 0 = none
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (oi >= 0 && (idx < 0 || ov < v || (ov == v && oi < idx))) { v = ov; idx = oi; }
-    }
+    // Three warp-wide integer reductions (REDUX) on an order-preserving 64-bit key instead of five rounds of three shuffles and a
+    // compare chain: the high word, the low word among the lanes that hold the smallest high word, then the index among those.
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);  // ascending as unsigned: negative values below positive ones
+    if (idx < 0) u = ~0ull;
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool mine = idx >= 0 && hi == mhi && lo == mlo;
+    const unsigned midx = __reduce_min_sync(0xffffffffu, mine ? (unsigned)idx : 0xffffffffu);
+    if (midx == 0xffffffffu) { idx = -1; return; }  // no candidate (v is left as it is)
+    unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+    m = (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
+    v = __longlong_as_double((long long)m);
+    idx = (int)midx;
 }
 template <int NW>
 struct MpcGroup;

@@ -21,13 +21,15 @@ ref[:, :, 5] = 0.28
 from optistate_b200.mpc import WarmStart  # noqa: E402
 
 rounds = int(os.environ.get("WARM_ROUNDS", "0"))
-for _ in range(2):
+best = float("inf")
+for _ in range(5):  # best of five: a process that has just started finds the GPU at idle clocks
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     kw = {"warm": False} if rounds < 0 else {}  # default: the dual active-set kernel with its warm start; WARM_ROUNDS=-1: cold
     xs, fs, mst, fst = estimate_state_mpc_batch(st["imu"], st["p"], st["dp"], st["contact"], ref, **kw)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    best = min(best, time.perf_counter() - t0)
+dt = best
 n = xs.shape[2]
 it = (mst >> 8).double()
 print("per step: warm accepted", [round(float((mst[t] & 8).ne(0).double().mean()), 2) for t in range(min(T, 12))], "ipm iterations", [round(float(it[t].mean()), 1) for t in range(min(T, 12))])
