@@ -36,10 +36,10 @@ __host__ __device__ constexpr int mpcg_slots(int nfl) { return nfl <= 2 ? 24 : (
 __host__ __device__ constexpr int mpcg_group(int nfl) { return nfl <= 2 ? 32 : 64; }  // threads per problem
 
 // per-problem shared memory (doubles): H^-1 [n][n|1] (Su [12][n] while H is built) | S^-1 [slots][slots+1] | x g | strip 2 x 64, after the
-// inversion y d r (three vectors of one entry per thread) | normals [3][threads] | block and id of a slot (2 ints per thread) | scratch 8
+// inversion y d r (three vectors of one entry per thread) | normals [3][threads] | block and id of a slot, list of the slots in use (3 ints per thread) | scratch 8
 __host__ __device__ constexpr int mpcg_problem_doubles(int nfl) {
     return mpcr_even((15 * nfl) * ((15 * nfl) | 1)) + mpcg_slots(nfl) * (mpcg_slots(nfl) + 1) + 2 * mpcg_group(nfl) +
-           (3 * mpcg_group(nfl) > 128 ? 3 * mpcg_group(nfl) : 128) + 3 * mpcg_group(nfl) + mpcg_group(nfl) + 8;
+           (3 * mpcg_group(nfl) > 128 ? 3 * mpcg_group(nfl) : 128) + 3 * mpcg_group(nfl) + mpcg_group(nfl) + mpcg_group(nfl) / 2 + 8;
 }
 __host__ __device__ constexpr size_t mpcg_smem_bytes() { return (size_t)MPCG_WARPS * mpcg_problem_doubles(2) * sizeof(double); }
 __host__ __device__ constexpr size_t mpcg2_smem_bytes(int max_legs) { return (size_t)mpcg_problem_doubles(max_legs) * sizeof(double); }
@@ -88,8 +88,8 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
     const int lane = G::tid();  // index in the group: row / slot / constraint block owned by this thread
     double *Ginv = base, *Su = base, *P = Ginv + mpcr_even(n * ldg), *xs = P + SLOTS * LDP, *g = xs + GT, *strip = g + GT;
     double *y = strip, *dslot = y + GT, *rslot = dslot + GT, *ncoef = strip + (3 * GT > 128 ? 3 * GT : 128);  // y, d, r reuse the strip once H is inverted
-    int *sblk = reinterpret_cast<int *>(ncoef + 3 * GT), *sid = sblk + GT;
-    double *scr = reinterpret_cast<double *>(sid + GT);
+    int *sblk = reinterpret_cast<int *>(ncoef + 3 * GT), *sid = sblk + GT, *slist = sid + GT;
+    double *scr = reinterpret_cast<double *>(slist + GT);
 
     int my_leg = 0;  // leg of the block this lane owns (blocks: stage-major, NFL legs per stage)
 #pragma unroll
@@ -139,6 +139,8 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
     using Mask = typename std::conditional<NW == 1, uint32_t, uint64_t>::type;  // one bit per slot
     const auto lowest = [](Mask mk) { return NW == 1 ? __ffs((int)mk) - 1 : __ffsll((long long)mk) - 1; };
     Mask valid = 0;  // slots in use
+    int q = 0;       // their number; slist[0 .. q) lists them in ascending order (loops over the working set are counted loops with
+                     // a broadcast load per slot - a bit scan per slot puts its latency on the loop-carried path)
     uint32_t inA = 0u;
     double uj = 0.0, nj0 = 0.0, nj1 = 0.0, nj2 = 0.0;
     int bj = 0, myid = -1;
@@ -149,13 +151,18 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double *gr = Ginv + row * ldg;  // this lane's row of H^-1
     const auto is_slot = [&]() { return ((valid >> lane) & Mask(1)) != 0; };
+    const auto relist = [&]() {  // after every change of `valid`; readers are separated from it by the next barrier
+        q = NW == 1 ? __popc((unsigned)valid) : __popcll((unsigned long long)valid);
+        if (is_slot()) slist[NW == 1 ? __popc((unsigned)(valid & ((Mask(1) << lane) - Mask(1)))) : __popcll((unsigned long long)(valid & ((Mask(1) << lane) - Mask(1))))] = lane;
+    };
     // r_j = sum_k S^-1[j][k] v[k] over the working slots (v in shared memory)
     const auto times_sinv = [&](const double *v) {
         double acc = 0.0;
         if (is_slot()) {
             const double *pr = P + lane * LDP;
-            for (Mask mk = valid; mk; mk &= mk - Mask(1)) {
-                const int k = lowest(mk);
+#pragma unroll 2
+            for (int t = 0; t < q; ++t) {
+                const int k = slist[t];
                 acc = fma(pr[k], v[k], acc);
             }
         }
@@ -168,8 +175,9 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
     const auto times_hinv_n = [&](const double *c) {
         double acc = 0.0;
         if constexpr (NW == 1) {
-            for (Mask mk = valid; mk; mk &= mk - Mask(1)) {
-                const int k = lowest(mk);
+#pragma unroll 2
+            for (int t = 0; t < q; ++t) {
+                const int k = slist[t];
                 const int bk = sblk[k];
                 const double hk = fma(gr[3 * bk + 2], ncoef[2 * GT + k], fma(gr[3 * bk + 1], ncoef[GT + k], gr[3 * bk] * ncoef[k]));
                 acc = fma(c[k], hk, acc);
@@ -204,16 +212,17 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
         if (is_slot()) {
             double *pr = P + lane * LDP;
             const double f = rj * idel;
-            for (Mask mk = valid; mk; mk &= mk - Mask(1)) {
-                const int k = lowest(mk);
+#pragma unroll 2
+            for (int t = 0; t < q; ++t) {
+                const int k = slist[t];
                 pr[k] = fma(f, rslot[k], pr[k]);
             }
             pr[s] = -f;
         }
         if (lane == s) {
             double *pr = P + s * LDP;
-            for (Mask mk = valid; mk; mk &= mk - Mask(1)) {
-                const int k = lowest(mk);
+            for (int t = 0; t < q; ++t) {
+                const int k = slist[t];
                 pr[k] = -rslot[k] * idel;
             }
             pr[s] = idel;
@@ -224,6 +233,8 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
         }
         valid |= Mask(1) << s;
         if (lane == bp) inA |= 1u << rp;
+        G::sync();  // every thread is done with the old list
+        relist();
     };
     // working constraint k leaves:  S^-1 <- S^-1 - S^-1[:, k] S^-1[k, :] / S^-1[k][k] on the remaining slots
     const auto leave = [&](int k) {
@@ -233,15 +244,18 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
             double *pr = P + lane * LDP;
             const double f = pr[k] * ipkk;
             const double *pk = P + k * LDP;
-            for (Mask mk = rest; mk; mk &= mk - Mask(1)) {
-                const int kk = lowest(mk);
-                pr[kk] = fma(-f, pk[kk], pr[kk]);
+#pragma unroll 2
+            for (int t = 0; t < q; ++t) {
+                const int kk = slist[t];
+                if (kk != k) pr[kk] = fma(-f, pk[kk], pr[kk]);
             }
         }
         const int idk = sid[k];
         if (lane == idk / 5) inA &= ~(1u << (idk % 5));
         if (lane == k) { uj = 0.0; myid = -1; }
         valid = rest;
+        G::sync();  // every thread is done with the old list
+        relist();
     };
 
     uint32_t pattern = 0;
