@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
     Real *noise = reinterpret_cast<Real *>(smem_raw + Smem::off_noise(n_lab, kRefRows));
     AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + Smem::off_acc(n_lab, kRefRows)) + tid;
 
+    if (grp_j * TMA_WARPS * S + tile_k * TW >= N) return;  // the whole block lies beyond the last trajectory (fewer trajectories than streams)
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);

@@ -435,6 +435,12 @@ def test_custom_model_constants_and_degenerate_sizes(algo):
     assert np.allclose(empty_t.x_final.cpu().numpy(), cases.START[:, None]) and np.allclose(empty_t.P_matrix()[0].cpu().numpy(), cases.Q_DEFAULT)
     empty_n = kf_batch(st["imu"], st["p"], st["dp"], st["contact"], st["f"], n_traj=0, algo=algo, outputs=("x_final",))
     assert empty_n.x_final.shape == (12, 0)
+    # fewer trajectories than streams on the streamed path (tiles of 32 streams): partly filled and empty tiles, several passes + a ragged one
+    wide = make_streams(range(40, 40 + 128), 30)
+    for n in (40, 100, 128 * 5 + 70):
+        got = kf_batch(wide["imu"], wide["p"], wide["dp"], wide["contact"], wide["f"], n_traj=n, algo=algo, outputs=("x_steps", "P_final"))
+        want = c_oracle.run(wide, n, want=("x_steps", "P_final"))
+        assert parity.rel_err(got.x_steps.cpu().numpy(), want["x_steps"]) < 1e-10 and parity.rel_err(got.P_final.cpu().numpy(), want["P_final"]) < 1e-10, n
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
