@@ -137,6 +137,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--e2e-upload", default="replicated", choices=["shared", "shared-lowprio", "replicated"],
+                    help="N > 1, e2e: every rank uploads all base streams (replicated), or 1/N of them + an NVLink all-gather on a "
+                         "high-priority NCCL stream (shared) / on NCCL's default stream (shared-lowprio)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: all-gather of the summaries fused into the filter kernel (NVLink peer stores) or NCCL after it")
     return ap.parse_args()
@@ -549,12 +552,30 @@ def run_native(a):
     if not a.no_e2e:
         from optistate_b200.pipeline import KfHostPipeline
 
-        pipe = KfHostPipeline(n_local, T, S, dtype=dtype, labels=("truth", "nominal"), stream_offset=first, structure=a.structure)
+        # N > 1: the ranks filter different members of the SAME base streams; with --e2e-upload shared each uploads 1/N of the stream
+        # arrays and the slices are exchanged over NVLink (pipeline.py); per-member noise and summaries are per rank
+        exchange_group = None
+        if world > 1 and a.e2e_upload != "replicated":
+            from optistate_b200.distributed import stream_exchange_group
+
+            exchange_group = stream_exchange_group() if a.e2e_upload == "shared" else dist.group.WORLD
+        pipe = KfHostPipeline(n_local, T, S, dtype=dtype, labels=("truth", "nominal"), stream_offset=first, structure=a.structure,
+                              shared_streams_group=exchange_group)
         for _ in range(max(2, a.warmup - 1)):
             step_e2e()
         finish_e2e()
         ms_e, _ = timed(step_e2e, a.steps, finish=finish_e2e)
-        h2d = sum(host[k].numel() * host[k].element_size() for k in ("imu", "p", "dp", "contact", "f", "truth", "nominal", "Q", "R"))
+        # outside the timed region: the summaries the host received are those of the device-resident path, bit for bit (also what
+        # checks the stream slices exchanged between the ranks in the shared upload mode)
+        last = pipe.submit(host)
+        got = pipe.result(last).clone()
+        kf_batch(d["imu"], d["p"], d["dp"], d["contact"], d["f"], **common)
+        torch.cuda.synchronize()
+        e2e_same = bool(torch.equal(got, out["summary"].cpu()))
+        if not e2e_same:
+            raise SystemExit("bench: the host pipeline's summaries differ from the device-resident path's")
+        h2d = pipe.h2d_bytes_per_batch  # counted from the copies this rank issued: all inputs at N = 1, its share of the streams + its noise at N > 1
+        assert world > 1 or h2d == sum(host[k].numel() * host[k].element_size() for k in ("imu", "p", "dp", "contact", "f", "truth", "nominal", "Q", "R"))
         if world > 1:
             tot = torch.tensor([float(h2d), float(nv.SUMMARY_ROWS * n_local * esz)], dtype=torch.float64, device=dev)
             dist.all_reduce(tot)
@@ -562,8 +583,9 @@ def run_native(a):
         else:
             h2d_total, d2h_total = h2d, nv.SUMMARY_ROWS * n_local * esz
         e2e = {"value": steps_total / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-               "ms_per_step": ms_e / a.steps,
-               "api": "optistate_b200.pipeline.KfHostPipeline (kf_batch on pinned host buffers, double-buffered)"}
+               "ms_per_step": ms_e / a.steps, "identical_to_resident_path": e2e_same, "upload": a.e2e_upload if world > 1 else "all inputs",
+               "api": "optistate_b200.pipeline.KfHostPipeline (kf_batch on pinned host buffers, double-buffered)" +
+                      ("; base streams uploaded once per job (1/N per rank) and all-gathered over NVLink" if pipe.world > 1 else "")}
 
     if peer is not None:
         peer.close()

@@ -24,6 +24,18 @@ def shard_sizes(n_total: int, world_size: int):
     return [shard_range(n_total, world_size, r)[1] - shard_range(n_total, world_size, r)[0] for r in range(world_size)]
 
 
+def stream_exchange_group(ranks=None):
+    """A process group for KfHostPipeline's exchange of base-stream slices (`shared_streams_group`): NCCL with HIGH-PRIORITY
+    streams, so that the all-gather of batch k+1's slices is scheduled as soon as a block of batch k's filter kernel retires
+    instead of queueing behind the whole kernel (the filter grid keeps every SM occupied for the length of a batch; on a
+    normal-priority stream the exchange ran only after it - measured: profiles/r2_e2e_upload_modes.txt).  gloo groups (CPU
+    tests of the host logic) have no such option and are returned as they are."""
+    if dist.get_backend() != "nccl":
+        return dist.new_group(ranks=ranks)
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+
+
 def gather_columns(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """All-gathers per-trajectory columns: local [C, n_local] on every rank -> [C, n_total] on every rank, in
     trajectory order.  Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""

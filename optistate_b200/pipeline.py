@@ -7,6 +7,11 @@ of batch k, so sustained end-to-end throughput is max(compute, copies) instead o
         ticket = pipe.submit(batch)
         ...
         summary = pipe.result(ticket)           # pinned host tensor [52, n_traj], valid until the slot is reused
+
+Several GPUs filtering different members of the SAME base streams (the Monte-Carlo sweep: one process per GPU, contiguous shards
+of the members): with `shared_streams_group` every rank uploads only its 1/world slice of the stream arrays over PCIe and the
+ranks exchange the slices over NVLink (one in-place NCCL all-gather per batch on the upload stream), so every byte of the
+streams crosses the host interface once per batch instead of once per GPU.  Per-member noise and summaries stay per rank.
 """
 from __future__ import annotations
 
@@ -23,7 +28,7 @@ _STREAM_CH = {"imu": 6, "p": 12, "dp": 12, "contact": 4, "f": 12, "truth": 12, "
 class KfHostPipeline:
     def __init__(self, n_traj: int, n_steps: int, n_streams: int, *, dtype: torch.dtype = torch.float64,
                  labels: Sequence[str] = ("truth", "nominal"), stream_offset: int = 0, n_slots: int = 2, device=None,
-                 structure: str = "auto"):
+                 structure: str = "auto", shared_streams_group=None):
         nv.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_traj, self.n_steps, self.n_streams, self.dtype = n_traj, n_steps, n_streams, dtype
@@ -31,16 +36,32 @@ class KfHostPipeline:
         self.structure = structure
         esz = 8 if dtype == torch.float64 else 4
         names = ["imu", "p", "dp", "contact", "f", *self.labels]
+        self.group, self.world, self.rank = shared_streams_group, 1, 0
+        if shared_streams_group is not None:
+            import torch.distributed as dist
+
+            self.world, self.rank = dist.get_world_size(shared_streams_group), dist.get_rank(shared_streams_group)
+        # the stream arrays of a slot live back to back in one allocation (padded to a multiple of the world size), so that a rank's
+        # share is one contiguous range of it
+        sizes = [n_steps * _STREAM_CH[k] * n_streams for k in names]
+        total = sum(sizes)
+        self._flat_len = (total + self.world - 1) // self.world * self.world
+        self._ranges, off = {}, 0
+        for k, n in zip(names, sizes):
+            self._ranges[k] = (off, off + n)
+            off += n
+        self.h2d_bytes_per_batch = 0  # what this rank copies from the host per submit (set below)
         self.slots = []
         for _ in range(n_slots):
-            dev = {k: torch.empty((n_steps, _STREAM_CH[k], n_streams), dtype=dtype, device=self.device) for k in names}
+            flat = torch.empty(self._flat_len, dtype=dtype, device=self.device)
+            dev = {k: flat[a:b].view(n_steps, _STREAM_CH[k], n_streams) for k, (a, b) in self._ranges.items()}
             dev["Q"] = torch.empty((12, n_traj), dtype=dtype, device=self.device)
             dev["R"] = torch.empty((10, n_traj), dtype=dtype, device=self.device)
             out = {"summary": torch.empty((nv.SUMMARY_ROWS, n_traj), dtype=dtype, device=self.device),
                    "status": torch.zeros(n_traj, dtype=torch.int32, device=self.device),
                    "workspace": torch.empty(n_steps * 10 * n_streams * esz + 4 * n_streams + 4096, dtype=torch.uint8, device=self.device)}
             host = torch.empty((nv.SUMMARY_ROWS, n_traj), dtype=dtype).pin_memory()
-            self.slots.append({"dev": dev, "out": out, "host": host, "ev_in": torch.cuda.Event(), "ev_k": torch.cuda.Event(),
+            self.slots.append({"dev": dev, "flat": flat, "out": out, "host": host, "ev_in": torch.cuda.Event(), "ev_k": torch.cuda.Event(),
                                "ev_out": torch.cuda.Event(), "busy": False})
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
         self._next = 0
@@ -56,8 +77,27 @@ class KfHostPipeline:
         with torch.cuda.stream(self.s_in):
             if slot["busy"]:
                 self.s_in.wait_event(slot["ev_k"])  # do not overwrite inputs a kernel may still be reading
-            for k, d in dev.items():
-                d.copy_(host[k], non_blocking=True)
+            copied = 0
+            if self.world == 1:
+                for k, d in dev.items():
+                    d.copy_(host[k], non_blocking=True)
+                    copied += d.numel()
+            else:
+                # this rank's share of the stream arrays over PCIe, the other shares over NVLink; noise is per rank
+                import torch.distributed as dist
+
+                flat, share = slot["flat"], self._flat_len // self.world
+                c0, c1 = self.rank * share, (self.rank + 1) * share
+                for k, (a, b) in self._ranges.items():
+                    lo, hi = max(a, c0), min(b, c1)
+                    if lo < hi:
+                        flat[lo:hi].copy_(host[k].reshape(-1)[lo - a:hi - a], non_blocking=True)
+                        copied += hi - lo
+                dist.all_gather_into_tensor(flat, flat[c0:c1], group=self.group)
+                for k in ("Q", "R"):
+                    dev[k].copy_(host[k], non_blocking=True)
+                    copied += dev[k].numel()
+            self.h2d_bytes_per_batch = copied * (8 if self.dtype == torch.float64 else 4)
             slot["ev_in"].record(self.s_in)
         with torch.cuda.stream(self.s_k):
             self.s_k.wait_event(slot["ev_in"])
