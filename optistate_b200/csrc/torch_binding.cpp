@@ -504,6 +504,106 @@ int64_t kf_host_call(const std::map<std::string, int64_t> &cfg, const std::map<s
     return 0;
 }
 
+
+// ---- the drop-in class's step (optistate_b200/kalman_filter.py) through ONE call of this binding ------------------------------
+// The class keeps one pinned host block with a FIXED layout (the offsets below, in doubles; kalman_filter.py mirrors them) and a device
+// block of the same size.  `ops` says which of the reference's methods run, in the reference's order: get_odom + the measurement
+// scatter (OPTI_KF_PHASE_MEASURE -> optistate_kf_measure), predict / predict_mpc (PHASE_PREDICT -> optistate_kf_batch, JOINT, dense
+// Q / R / P like the class holds them) and update (PHASE_UPDATE).  PREDICT | UPDATE runs the update on the prediction's outputs in the
+// same call (two launches, no host round trip in between) and returns both results: the class hands out the second one when its
+// update() finds state and measurement untouched since.  One stream synchronisation per call.
+// `mode`: 0 = inputs uploaded and outputs downloaded with asynchronous copies; 1 = inputs uploaded, the kernels write their outputs and
+// status words straight into the pinned host block (zero-copy stores over PCIe, no download); 2 = the kernels also read their inputs
+// from the pinned block (no upload either).
+enum : int64_t {
+    CS_X = 0, CS_P = 12, CS_Q = 156, CS_R = 300, CS_FEET = 400, CS_F = 412, CS_Z = 424, CS_BREF = 434, CS_IMU = 446, CS_DP = 452,
+    CS_CONTACT = 464, CS_IN_END = 468,
+    CS_PRED_X = 468, CS_PRED_P = 480, CS_PRED_FEET = 624, CS_PRED_TRACE = 636,
+    CS_UPD_X = 637, CS_UPD_P = 649, CS_UPD_K = 793, CS_UPD_TRACE = 913, CS_UPD_KGAIN = 914,
+    CS_ODOM = 915, CS_END = 919, CS_TOTAL = 920
+};
+
+int64_t kf_class_step(int64_t ops, int64_t cov_model, const std::vector<double> &consts, at::Tensor h_block, at::Tensor d_block,
+                      at::Tensor h_status, at::Tensor d_status, int64_t mode) {
+    TORCH_CHECK(d_block.is_cuda() && d_status.is_cuda(), "optistate_b200: device buffers must be CUDA tensors (there is no CPU path)");
+    TORCH_CHECK(h_block.is_pinned() && h_status.is_pinned(), "optistate_b200: host buffers must be pinned");
+    TORCH_CHECK(h_block.scalar_type() == at::kDouble && d_block.scalar_type() == at::kDouble && h_block.numel() >= CS_TOTAL &&
+                    d_block.numel() >= CS_TOTAL && h_block.is_contiguous() && d_block.is_contiguous(), "optistate_b200: bad state block");
+    TORCH_CHECK(h_status.scalar_type() == at::kInt && d_status.scalar_type() == at::kInt && h_status.numel() >= 4 && d_status.numel() >= 4,
+                "optistate_b200: bad status block");
+    TORCH_CHECK(consts.size() == 6 && mode >= 0 && mode <= 2, "optistate_b200: bad arguments");
+    const c10::cuda::CUDAGuard guard(d_block.device());
+    cudaStream_t stream = at::cuda::getCurrentCUDAStream().stream();
+    double *host = h_block.data_ptr<double>(), *dev = d_block.data_ptr<double>(), *host_alias = nullptr;
+    uint32_t *hst = reinterpret_cast<uint32_t *>(h_status.data_ptr<int32_t>()), *dst = reinterpret_cast<uint32_t *>(d_status.data_ptr<int32_t>()),
+             *hst_alias = nullptr;
+    if (mode >= 1) {
+        TORCH_CHECK(cudaHostGetDevicePointer((void **)&host_alias, host, 0) == cudaSuccess && cudaHostGetDevicePointer((void **)&hst_alias, hst, 0) == cudaSuccess,
+                    "optistate_b200: the pinned block is not mapped into the device's address space");
+    }
+    const double *in = mode == 2 ? host_alias : dev;
+    double *out = mode >= 1 ? host_alias : dev;
+    uint32_t *st = mode >= 1 ? hst_alias : dst;
+    hst[0] = hst[1] = hst[2] = 0;  // [0] predict, [1] update, [2] measure
+    if (mode < 2) TORCH_CHECK(cudaMemcpyAsync(dev, host, CS_IN_END * sizeof(double), cudaMemcpyHostToDevice, stream) == cudaSuccess, "upload failed");
+    if (mode == 0) TORCH_CHECK(cudaMemsetAsync(dst, 0, 4 * sizeof(uint32_t), stream) == cudaSuccess, "memset failed");
+    if (ops & OPTI_KF_PHASE_MEASURE) {
+        OptiKfMeasureDesc m;
+        std::memset(&m, 0, sizeof m);
+        m.struct_size = sizeof m;
+        m.abi_version = OPTISTATE_KF_ABI_VERSION;
+        m.dtype = OPTI_KF_F64;
+        m.n_steps = 1;
+        m.n_streams = 1;
+        m.imu = in + CS_IMU; m.p = in + CS_FEET; m.dp = in + CS_DP; m.contact = in + CS_CONTACT;
+        m.odom = out + CS_ODOM;
+        m.status = st + 2;
+        const int rc = optistate_kf_measure(&m, stream);
+        if (rc != 0) return rc;
+    }
+    OptiKfDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.abi_version = OPTISTATE_KF_ABI_VERSION;
+    d.dtype = OPTI_KF_F64;
+    d.algo = OPTI_KF_ALGO_JOINT;
+    d.n_traj = d.n_steps = d.n_streams = 1;
+    d.dt = consts[0]; d.mass = consts[1]; d.inertia[0] = consts[2]; d.inertia[1] = consts[3]; d.inertia[2] = consts[4]; d.gravity = consts[5];
+    d.p0_kind = d.q_kind = d.r_kind = OPTI_KF_MAT_DENSE;
+    d.Q = in + CS_Q;
+    d.R = in + CS_R;
+    if (ops & OPTI_KF_PHASE_PREDICT) {
+        OptiKfDesc p = d;
+        p.phases = OPTI_KF_PHASE_PREDICT;
+        p.cov_model = (int32_t)cov_model;
+        p.x0 = in + CS_X; p.P0 = in + CS_P; p.p = in + CS_FEET; p.f = in + CS_F;
+        if (cov_model == OPTI_KF_COV_MPC) p.body_ref = in + CS_BREF;
+        p.x_final = out + CS_PRED_X; p.P_final = out + CS_PRED_P; p.p_world_steps = out + CS_PRED_FEET; p.p_trace_steps = out + CS_PRED_TRACE;
+        p.status = st + 0;
+        const int rc = optistate_kf_batch(&p, stream);
+        if (rc != 0) return rc;
+    }
+    if (ops & OPTI_KF_PHASE_UPDATE) {
+        OptiKfDesc u = d;
+        u.phases = OPTI_KF_PHASE_UPDATE;
+        const bool chained = ops & OPTI_KF_PHASE_PREDICT;  // the update of the state the prediction above has just written
+        u.x0 = chained ? out + CS_PRED_X : in + CS_X;
+        u.P0 = chained ? out + CS_PRED_P : in + CS_P;
+        u.z_in = in + CS_Z;
+        u.x_final = out + CS_UPD_X; u.P_final = out + CS_UPD_P; u.K_final = out + CS_UPD_K; u.p_trace_steps = out + CS_UPD_TRACE;
+        u.k_gain_steps = out + CS_UPD_KGAIN;
+        u.status = st + 1;
+        const int rc = optistate_kf_batch(&u, stream);
+        if (rc != 0) return rc;
+    }
+    if (mode == 0) {
+        TORCH_CHECK(cudaMemcpyAsync(host + CS_IN_END, dev + CS_IN_END, (CS_END - CS_IN_END) * sizeof(double), cudaMemcpyDeviceToHost, stream) == cudaSuccess, "download failed");
+        TORCH_CHECK(cudaMemcpyAsync(hst, dst, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream) == cudaSuccess, "download failed");
+    }
+    TORCH_CHECK(cudaStreamSynchronize(stream) == cudaSuccess, "optistate_b200: the launch failed");
+    return 0;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -511,6 +611,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kf_batch", &kf_batch);
     m.def("kf_measure", &kf_measure);
     m.def("kf_host_call", &kf_host_call);
+    m.def("kf_class_step", &kf_class_step);
     m.def("kf_resolve_algo", &kf_resolve_algo);
     m.def("fma_peak", &fma_peak);
     m.def("kf_identify_noise", &kf_identify_noise);

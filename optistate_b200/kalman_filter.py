@@ -20,6 +20,8 @@ with qpOASES unpinned, see there), unless forces are passed explicitly (`f=`) or
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -27,6 +29,7 @@ from . import _native as nv
 from .settings import INITIAL_PARAMS
 
 _SEL = [0, 1, 2, 5, 6, 7, 8, 9, 10, 11]
+_F8 = np.dtype(np.float64)
 
 
 class Kalman_Filter:
@@ -74,77 +77,77 @@ class Kalman_Filter:
         nv.require_cuda()
         return torch.device("cuda", torch.cuda.current_device()) if self._device is None else torch.device(self._device)
 
-    def _consts(self):
-        I = np.asarray(self.inertia_rot, float)
-        return dict(dt=float(self.dt), mass=float(self.m), inertia0=float(I[0, 0]), inertia1=float(I[1, 1]),
-                    inertia2=float(I[2, 2]), gravity=float(np.asarray(self.g, float).reshape(12)[11]))
-
     @staticmethod
     def _col(a, n):
         return np.asarray(a, dtype=np.float64).reshape(n)
 
-    # One pinned host buffer and one device buffer each way, allocated once per instance: a call is then one asynchronous
-    # host->device copy, one launch, two asynchronous device->host copies (values, status) and ONE stream synchronisation,
-    # issued by the binding (kf_host_call) below the Python dispatcher - no allocation, no pageable staging copy, no
-    # device-side concatenation (which cost the first version ~110 us per call).
-    _IN_MAX = 12 + 144 + 144 + 100 + 12 + 12 + 12 + 10 + 6 + 12 + 4
-    _OUT_SIZES = {"x_final": 12, "P_final": 144, "K_final": 120, "p_world_steps": 12, "p_trace_steps": 1, "k_gain_steps": 1, "odom": 4}
-    _OUT_MAX = 12 + 144 + 120 + 12 + 1 + 1 + 4
+    # One pinned host block with a fixed layout (inputs, then the outputs of predict / update / get_odom; offsets shared with
+    # csrc/torch_binding.cpp:kf_class_step) and one device block, allocated once per instance.  A method packs its inputs through
+    # NumPy views of the block, makes ONE call of the binding (upload, launches, results, one stream synchronisation - all below the
+    # Python dispatcher) and reads its outputs from views again.  `transfer` picks how the bytes cross the host interface:
+    # "copy" = asynchronous copies both ways, "store" = the kernels write results and status straight into the pinned block
+    # (zero-copy stores, no download), "mapped" = they read their inputs from it as well (no upload either).
+    # predict / predict_mpc also run the update that normally follows them, on the prediction's outputs and the current z and R, in
+    # the same call (two launches back to back, no host round trip between them); update() hands that result out when x, P, z and R
+    # are still what that launch saw, and launches on its own otherwise - same values either way (same kernel, same inputs).
+    _LAYOUT = {"x": (0, 12), "P": (12, 144), "Q": (156, 144), "R": (300, 100), "p": (400, 12), "f": (412, 12), "z": (424, 10),
+               "body_ref": (434, 12), "imu": (446, 6), "dp": (452, 12), "contact": (464, 4),
+               "pred_x": (468, 12), "pred_P": (480, 144), "pred_p_world": (624, 12), "pred_trace": (636, 1),
+               "upd_x": (637, 12), "upd_P": (649, 144), "upd_K": (793, 120), "upd_trace": (913, 1), "upd_kgain": (914, 1), "odom": (915, 4)}
+    _BLOCK = 920
+    _MODES = {"copy": 0, "store": 1, "mapped": 2}
+    transfer = "store"
+
+    _v = None
 
     def _buffers(self):
-        dev = self._dev()
-        if getattr(self, "_buf_dev", None) != dev:
-            self._buf_dev = dev
-            self._h_in = torch.empty(self._IN_MAX, dtype=torch.float64).pin_memory()
-            self._h_in_np = self._h_in.numpy()
-            self._d_in = torch.empty(self._IN_MAX, dtype=torch.float64, device=dev)
-            self._d_out = torch.empty(self._OUT_MAX, dtype=torch.float64, device=dev)
-            self._h_out = torch.empty(self._OUT_MAX, dtype=torch.float64).pin_memory()
-            self._h_out_np = self._h_out.numpy()
-            self._d_status = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._h_status_np = self._h_status.numpy()
-        return dev
+        if self._v is None:  # first device call of this instance: the blocks live on the device that is current now (or `device`)
+            dev = self._dev()
+            self._h_block = torch.zeros(self._BLOCK, dtype=torch.float64).pin_memory()
+            self._d_block = torch.zeros(self._BLOCK, dtype=torch.float64, device=dev)
+            self._h_status = torch.zeros(4, dtype=torch.int32).pin_memory()
+            self._d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+            blk = self._h_block.numpy()
+            self._v = {k: blk[o:o + n] for k, (o, n) in self._LAYOUT.items()}
+            shapes = {"P": (12, 12), "Q": (12, 12), "R": (10, 10)}
+            self._vs = {k: v.reshape(shapes.get(k, (v.size, 1))) for k, v in self._v.items()}
+            self._st = self._h_status.numpy()
+            self._call = nv.ext().kf_class_step
+            self._ahead = None
 
-    def _launch(self, host_in, want, cfg, consts):
-        """Packs `host_in` (name -> array, in order) into the pinned buffer; the binding uploads, launches (kf_batch with `cfg`, or
-        kf_measure when cfg is empty), downloads the `want` outputs and the status word and synchronises.  Returns {name: NumPy copy}."""
-        self._buffers()
-        in_layout, off = [], 0
-        for k, v in host_in.items():
-            n = v.size
-            self._h_in_np[off:off + n] = v.reshape(-1)
-            in_layout.append((k, n))
-            off += n
-        out_layout = [(k, self._OUT_SIZES[k]) for k in want]
-        nv.check(int(nv.ext().kf_host_call(cfg, consts, in_layout, out_layout, self._h_in, self._d_in, self._d_out, self._h_out,
-                                            self._d_status, self._h_status)), "optistate_kf_batch" if cfg else "optistate_kf_measure")
-        self.status = int(self._h_status_np[0])
-        res, off = {}, 0
-        for k, n in out_layout:
-            res[k] = self._h_out_np[off:off + n].copy()
-            off += n
-        return res
+    def _put(self, name, a, n):
+        v = self._vs[name]  # the view in the shape the reference's arrays have: no reshape on the common path
+        if type(a) is np.ndarray and a.shape == v.shape:
+            v[...] = a
+        else:
+            self._v[name][:] = np.asarray(a, dtype=np.float64).reshape(n)
 
-    def _step(self, phases, cov_model, host_in, want):
-        """One trajectory, one step through optistate_kf_batch (JOINT)."""
-        cfg = dict(dtype=nv.F64, algo=nv.ALGO_JOINT, cov_model=cov_model, phases=phases, n_traj=1, n_steps=1, n_streams=1,
-                   x0_per_traj=0, p0_kind=nv.MAT_DENSE, q_kind=nv.MAT_DENSE, r_kind=nv.MAT_DENSE)
-        return self._launch(host_in, want, cfg, self._consts())
+    def _run(self, ops, cov_model=nv.COV_PREDICT):
+        I, g = self.inertia_rot, self.g
+        consts = [float(self.dt), float(self.m), float(I[0][0]), float(I[1][1]), float(I[2][2]), float(g[11][0] if np.ndim(g) == 2 else g[11])]
+        nv.check(int(self._call(ops, cov_model, consts, self._h_block, self._d_block, self._h_status, self._d_status, self._MODES[self.transfer])),
+                 "optistate_kf_measure" if ops == nv.PHASE_MEASURE else "optistate_kf_batch")
 
-    def _state_in(self):
-        return {"x0": self._col(self.x, 12), "P0": np.asarray(self.P, dtype=np.float64).reshape(144),
-                "Q": np.asarray(self.Q, dtype=np.float64).reshape(144), "R": np.asarray(self.R, dtype=np.float64).reshape(100)}
+    def _put_state(self):
+        self._put("x", self.x, 12)
+        self._put("P", self.P, 144)
+        self._put("Q", self.Q, 144)
+        self._put("R", self.R, 100)
 
     # ------------------------------------------------------------------ reference surface
     def get_odom(self, p_cur, dp_cur, contact_cur, imu):
         """kalman_filter.py:79-105 -> (4,1) array [z, vx, vy, vz]."""
-        host_in = {"imu": self._col(imu, 6), "p": self._col(p_cur, 12), "dp": self._col(dp_cur, 12), "contact": self._col(contact_cur, 4)}
-        r = self._launch(host_in, ["odom"], {}, {})
+        self._buffers()
+        self._put("imu", imu, 6)
+        self._put("p", p_cur, 12)
+        self._put("dp", dp_cur, 12)
+        self._put("contact", contact_cur, 4)
+        self._run(nv.PHASE_MEASURE)
+        self.status = int(self._st[2])
         if self.status & nv.ST_ALL_SWING:
             raise ValueError("setting an array element with a sequence. The requested array has an inhomogeneous shape "
                              "(all four feet in swing; the reference fails here too, kalman_filter.py:97-103)")
-        return r["odom"].reshape(4, 1)
+        return self._v["odom"].copy().reshape(4, 1)
 
     def set_measurements(self, imu, odom):
         """kalman_filter.py:108-117 (in-place scatter into self.z)."""
@@ -155,22 +158,43 @@ class Kalman_Filter:
         self.z[7:10] = odom[1:].reshape(3, 1)
 
     def _refresh_model_matrices(self, angles, exp_form):
-        R = self.rotation_matrix_body_world(angles[0], angles[1], angles[2])
-        self.F[0:3, 6:9] = np.transpose(R)
+        """The host-side attributes the reference refreshes in predict / predict_mpc (kalman_filter.py:125-128,153-157): F carries R^T,
+        F_d and B_d are rebound to new arrays.  (The filter evaluates its own R on the device; this is bookkeeping for callers that read them.)"""
+        a, b, c = float(angles[0]), float(angles[1]), float(angles[2])
+        sa, ca, sb, cb, sc, cc = math.sin(a), math.cos(a), math.sin(b), math.cos(b), math.sin(c), math.cos(c)
+        self.F[0:3, 6:9] = ((cc * cb, sc * cb, -sb),
+                            (cc * (sb * sa) - sc * ca, sc * (sb * sa) + cc * ca, cb * sa),
+                            (cc * (sb * ca) + sc * sa, sc * (sb * ca) - cc * sa, cb * ca))
         self.F_d = np.exp(self.dt * self.F) if exp_form else self.identity_large + self.dt * self.F
         self.B_d = self.dt * self.B
+
+    def _predict_call(self, p, f, cov_model, body_ref=None):
+        """The device part of predict / predict_mpc, with the update that follows it computed ahead (see _buffers)."""
+        self._buffers()
+        self._put_state()
+        self._put("p", p, 12)
+        self._put("f", f, 12)
+        self._put("z", self.z, 10)
+        if body_ref is not None:
+            self._put("body_ref", body_ref, 12)
+        self._ahead = None
+        self._run(nv.PHASE_PREDICT | nv.PHASE_UPDATE, cov_model)
+        v = self._v
+        self.status = int(self._st[0])
+        p[...] = v["pred_p_world"].reshape(np.shape(p))
+        self.x = v["pred_x"].copy().reshape(12, 1)
+        self.P = v["pred_P"].copy().reshape(12, 12)
+        self.x_model = self.x.copy()
+        # what update() must still find in place to hand out the result computed ahead: the state this call produced, and the z and R
+        # the second launch read (compared as bytes: stricter than ==, and cheap)
+        self._ahead = (self.x.tobytes(), self.P.tobytes(), v["z"].tobytes(), v["R"].tobytes())
 
     def predict(self, p, f):
         """kalman_filter.py:119-138; p (12,1) is rotated into the world frame in place."""
         prior = self._col(self.x, 12).copy()
-        host_in = dict(self._state_in(), p=self._col(p, 12), f=self._col(f, 12))
-        r = self._step(nv.PHASE_PREDICT, nv.COV_PREDICT, host_in, ["x_final", "P_final", "p_world_steps", "p_trace_steps"])
+        self._predict_call(p, f, nv.COV_PREDICT)
         self._refresh_model_matrices(prior[0:3], exp_form=False)
-        p[...] = r["p_world_steps"].reshape(np.shape(p))
-        self.x = r["x_final"].reshape(12, 1)
-        self.P = r["P_final"].reshape(12, 12)
-        self.x_model = self.x.copy()
-        self.P_trace = float(r["p_trace_steps"][0])
+        self.P_trace = float(self._v["pred_trace"][0])
 
     def predict_mpc(self, p, body_ref, cur_contact, f=None):
         """kalman_filter.py:140-162 with the QP replaced by `force_provider` (or an explicit f):
@@ -199,25 +223,34 @@ class Kalman_Filter:
         f0 = self.f[:, 0].reshape(12)
         body_ref = np.asarray(body_ref, float)
         br = body_ref[:, 0] if body_ref.ndim == 2 and body_ref.shape[1] > 1 else body_ref.reshape(12)
-        host_in = dict(self._state_in(), p=self._col(p, 12), f=f0, body_ref=br.reshape(12))
-        r = self._step(nv.PHASE_PREDICT, nv.COV_MPC, host_in, ["x_final", "P_final", "p_world_steps", "p_trace_steps"])
+        self._predict_call(p, f0, nv.COV_MPC, body_ref=br)
         self._refresh_model_matrices(br[0:3], exp_form=True)
-        p[...] = r["p_world_steps"].reshape(np.shape(p))
-        self.x = r["x_final"].reshape(12, 1)
-        self.P = r["P_final"].reshape(12, 12)
-        self.x_model = self.x.copy()
+
+    @staticmethod
+    def _bytes(a):
+        return a.tobytes() if type(a) is np.ndarray and a.dtype == _F8 else None
+
+    def _ahead_is_valid(self):
+        a, b = self._ahead, self._bytes
+        return a is not None and b(self.x) == a[0] and b(self.P) == a[1] and b(self.z) == a[2] and b(self.R) == a[3]
 
     def update(self):
         """kalman_filter.py:164-174."""
-        host_in = dict(self._state_in(), z_in=self._col(self.z, 10))
-        r = self._step(nv.PHASE_UPDATE, nv.COV_PREDICT, host_in, ["x_final", "P_final", "K_final", "p_trace_steps", "k_gain_steps"])
+        self._buffers()
+        if not self._ahead_is_valid():  # x, P, z or R were changed after the prediction (or there was none): update on its own
+            self._put_state()
+            self._put("z", self.z, 10)
+            self._run(nv.PHASE_UPDATE)
+        self._ahead = None
+        v = self._v
+        self.status = int(self._st[1])
         if self.status & nv.ST_SINGULAR:  # np.linalg.inv raises for a singular S only; an indefinite one goes through (kalman_filter.py:168)
             raise np.linalg.LinAlgError("Singular matrix")
-        self.K = r["K_final"].reshape(12, 10)
-        self.x = r["x_final"].reshape(12, 1)
-        self.P = r["P_final"].reshape(12, 12)
-        self.P_trace = float(r["p_trace_steps"][0])
-        self.K_gain = float(r["k_gain_steps"][0])
+        self.K = v["upd_K"].copy().reshape(12, 10)
+        self.x = v["upd_x"].copy().reshape(12, 1)
+        self.P = v["upd_P"].copy().reshape(12, 12)
+        self.P_trace = float(v["upd_trace"][0])
+        self.K_gain = float(v["upd_kgain"][0])
 
     def estimate_state_mpc(self, imu, p, dp, body_ref, contact, f=None):
         """kalman_filter.py:176-182."""

@@ -110,3 +110,67 @@ def test_error_conventions():
     # the attributes of the reference's MPC set-up exist with its shapes (kalman_filter.py:37-43,73-77)
     assert kf3.p_mpc.shape == (12, 6) and kf3.body_mpc.shape == (12, 6) and kf3.contact_mpc.shape == (4, 5)
     assert kf3.zero_mat.shape == (3, 3) and np.array_equal(kf3.identity, np.eye(3)) and np.allclose(kf3.identity_m, np.eye(3) / kf3.m)
+
+
+@pytest.mark.parametrize("transfer", ["copy", "store", "mapped"])
+def test_every_transfer_mode_gives_the_same_numbers(transfer):
+    """How the bytes of a call cross the host interface (asynchronous copies, zero-copy stores, zero-copy loads and stores) is
+    plumbing: every mode reproduces the golden of the unmodified reference class."""
+    stream, kw, _ = cases.build("cfg1_default_seed0")
+    g = cases.load_golden("cfg1_default_seed0")
+    kf = Kalman_Filter()
+    kf.transfer = transfer
+    kf.x = kf.x.copy()
+    xs, pws, tr, kg = drive(kf, stream, 25)
+    assert np.abs(xs - g["x"][:25]).max() < 1e-12 and np.abs(pws - g["p_world"][:25]).max() < 1e-13
+    assert np.abs(tr / g["p_trace"][:25] - 1).max() < 1e-12 and np.abs(kg / g["k_gain"][:25] - 1).max() < 1e-12
+
+
+def test_update_computed_ahead_is_only_used_when_nothing_changed():
+    """predict() launches the update that normally follows it in the same call; update() may hand that result out only if x, P, z
+    and R are what that launch read.  A caller that touches any of them between the two calls gets an update of what it set."""
+    from optistate_b200 import _native as nv
+
+    stream, _, _ = cases.build("cfg1_default_seed0")
+    cols = {k: stream[k][3].reshape(-1, 1).copy() for k in ("imu", "p", "dp", "contact", "f")}
+
+    def fresh():
+        kf = Kalman_Filter()
+        kf.x = kf.x.copy()
+        kf.P = kf.P.copy()
+        kf.set_measurements(cols["imu"], kf.get_odom(cols["p"], cols["dp"], cols["contact"], cols["imu"]))
+        kf.predict(cols["p"].copy(), cols["f"])
+        return kf
+
+    # untouched: no launch in update(), and the numbers are those of an update launched on its own
+    a, b = fresh(), fresh()
+    before = nv.ext().launch_count()
+    a.update()
+    assert nv.ext().launch_count() == before
+    b._ahead = None
+    b.update()
+    assert nv.ext().launch_count() == before + 1
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.P, b.P) and np.array_equal(a.K, b.K) and a.K_gain == b.K_gain and a.P_trace == b.P_trace
+
+    def host_update(kf):
+        H = np.asarray(kf.H, float)
+        x, P, z, R = (np.array(v, dtype=float) for v in (kf.x, kf.P, kf.z, kf.R))
+        K = P @ H.T @ np.linalg.inv(H @ P @ H.T + R)
+        return x + K @ (z - H @ x), (np.eye(12) - K @ H) @ P
+
+    # every input of the update, changed in place or rebound after the prediction, is honoured
+    for change in ("z_in_place", "x_in_place", "P_rebound", "R_rebound"):
+        kf = fresh()
+        if change == "z_in_place":
+            kf.z[3] += 0.05
+        elif change == "x_in_place":
+            kf.x[9:12] += 0.1
+        elif change == "P_rebound":
+            kf.P = kf.P * 1.5
+        else:
+            kf.R = np.asarray(kf.R) * 2.0
+        want_x, want_P = host_update(kf)
+        before = nv.ext().launch_count()
+        kf.update()
+        assert nv.ext().launch_count() == before + 1, change
+        assert np.abs(kf.x - want_x).max() < 1e-11 and np.abs(kf.P - want_P).max() < 1e-12, change

@@ -7,4 +7,12 @@ import bench  # noqa: E402
 from optistate_b200.synth import make_streams  # noqa: E402
 
 if __name__ == "__main__":
-    print(bench.dropin_rate(make_streams(range(1), 400)))
+    st = make_streams(range(1), 400)
+    for mode in ("copy", "store", "mapped"):
+        print(bench.dropin_rate(st, transfer=mode))
+    if "--profile" in sys.argv:
+        import cProfile
+        import pstats
+
+        cProfile.run("bench.dropin_rate(st)", "/tmp/dropin.prof")
+        pstats.Stats("/tmp/dropin.prof").sort_stats("tottime").print_stats(12)
