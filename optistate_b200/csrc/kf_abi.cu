@@ -140,6 +140,11 @@ bool packed_pair_ok(const OptiKfDesc *d) {
 
 template <typename Real>
 int launch_streamed_t(const OptiKfDesc *d, const okf::Params<typename okf::Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    if constexpr (okf::Lanes<Real>::n == 1) {
+        // no more trajectories than streams: every block would hold one working warp - the one-warp-per-block latency variant
+        if (p.block && p.N <= p.S && p.cov_model == OPTI_KF_COV_PREDICT)
+            return d->summary ? okf::launch_seq_tma_lone<Real, true>(p, stream) : okf::launch_seq_tma_lone<Real, false>(p, stream);
+    }
     if (p.block) return d->summary ? okf::launch_seq_tma<Real, true, true>(p, stream) : okf::launch_seq_tma<Real, false, true>(p, stream);
     return d->summary ? okf::launch_seq_tma<Real, true, false>(p, stream) : okf::launch_seq_tma<Real, false, false>(p, stream);
 }

@@ -15,6 +15,11 @@ namespace okf {
 template <typename Real, bool kSummary, bool kBlock>
 int launch_seq_tma(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream);
 
+// The same kernel with one warp per block, for batches with no more trajectories than streams (a lone warp per scheduler: latency,
+// not throughput, decides); Real = double | float, decoupled-group form and predict() covariance model only.
+template <typename Real, bool kSummary>
+int launch_seq_tma_lone(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream);
+
 // Direct-load SEQUENTIAL kernel (kf_seq.cuh).
 template <typename Real>
 int launch_seq_direct(const Params<Real> &p, cudaStream_t stream);

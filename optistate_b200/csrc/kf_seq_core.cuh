@@ -237,6 +237,19 @@ __device__ __forceinline__ Real gain_trace(const Real (&P)[NP], const Real *r, i
     return g;
 }
 
+// The same with the reciprocals of r supplied (taken once per trajectory by the kernels that write K_gain every step), in two
+// interleaved sums: half the dependent chain, no reciprocal in the time loop.
+template <bool kBlock = false, typename Real>
+__device__ __forceinline__ Real gain_trace_rinv(const Real (&P)[NP], const Real *rinv, int stride) {
+    Real g0 = Real(0), g1 = Real(0);
+#pragma unroll
+    for (int j = 0; j < NZ; j += 2) {
+        if (cpl<kBlock>(j, sel(j))) g0 = fma_(P[tri(j, sel(j))], rinv[j * stride], g0);
+        if (cpl<kBlock>(j + 1, sel(j + 1))) g1 = fma_(P[tri(j + 1, sel(j + 1))], rinv[(j + 1) * stride], g1);
+    }
+    return g0 + g1;
+}
+
 // cheap test whether trunc(R^T) can have a non-zero entry in any lane (then the exact decision is taken per lane)
 template <typename Real>
 __device__ __forceinline__ bool may_truncate(const Real (&R)[9]) {

@@ -49,6 +49,11 @@ __host__ __device__ constexpr int tma_threads() { return 32 * tma_warps<kBlock>(
 constexpr int TMA_CH_G0 = 24, TMA_CH_G1 = 10;
 constexpr int TMA_CH_REF = 3;  // reference body angles of the predict_mpc covariance model (kMpc kernels), part of group G0
 constexpr int TMA_NOISE_ROWS = 22;  // q[12] r[10]
+constexpr int TMA_NOISE_ROWS_OUT = 32;  // ... and 1 / r[10] in the instantiations with per-step outputs (K_gain every step)
+template <int kW>
+__host__ __device__ constexpr int tma_stages() { return kW == 1 ? 2 : 1; }
+template <int kOut>
+__host__ __device__ constexpr int tma_noise_rows() { return kOut != 0 ? TMA_NOISE_ROWS_OUT : TMA_NOISE_ROWS; }
 constexpr int TMA_ACC_ROWS = 25;    // running sums of the summary: 0-11 truth, 12-23 nominal, 24 NIS
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,15 +91,15 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const CUtensorMap *map, 
                  : "memory");
 }
 
-template <typename Real, int kThreads>
+template <typename Real, int kThreads, int kNoiseRows = TMA_NOISE_ROWS, int kStages = 1>
 struct TmaSmem {
-    // dynamic shared memory: [mbarriers + counters 128 B][G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] (one tile
-    //                        set per block)  [noise [22][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
+    // dynamic shared memory: [mbarriers + counters 128 B][G0 [24][32] | G1 [10][32] | G2 [12*n_lab][32] | ref [ref_rows][32]] (kStages tile
+    //                        sets per block)  [noise [22 | 32][128]][acc [25][128] (8-byte sums; double and F2 kernels only)]   (elements: Real)
     static __host__ __device__ constexpr size_t warp_rows(int n_lab, int ref_rows) { return TMA_CH_G0 + TMA_CH_G1 + 12 * n_lab + ref_rows; }
     static __host__ __device__ constexpr size_t warp_bytes(int n_lab, int ref_rows) { return warp_rows(n_lab, ref_rows) * 32 * sizeof(Real); }
     static __host__ __device__ constexpr size_t off_in() { return 128; }
-    static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + warp_bytes(n_lab, ref_rows); }
-    static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)TMA_NOISE_ROWS * kThreads * sizeof(Real); }
+    static __host__ __device__ constexpr size_t off_noise(int n_lab, int ref_rows) { return off_in() + kStages * warp_bytes(n_lab, ref_rows); }
+    static __host__ __device__ constexpr size_t off_acc(int n_lab, int ref_rows) { return off_noise(n_lab, ref_rows) + (size_t)kNoiseRows * kThreads * sizeof(Real); }
     static __host__ __device__ constexpr size_t total(int n_lab, int ref_rows, bool acc_in_smem) {
         return off_acc(n_lab, ref_rows) + (acc_in_smem ? (size_t)TMA_ACC_ROWS * kThreads * 8 : 0);
     }
@@ -150,17 +155,26 @@ __host__ __device__ constexpr bool tma_acc_in_smem() {
     return kSummary && sizeof(Real) == 8;
 }
 
-template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock = false>
-__global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kSummary, kBlock>()) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
+// kW: warps per block; 0 = the throughput geometry above (tma_warps).  kW = 1 is the LATENCY variant, chosen by the host when there are
+// no more trajectories than streams (every block of the throughput geometry would hold one working warp - BASELINE configs[1],
+// 1,024 trajectories x 10,000 steps, is the case): a block is its one warp, so nobody counts readers (no shared-memory atomic, whose
+// warp-aggregated expansion put ~100 dependent cycles three times into every step of a lone warp), the running sums of the summary
+// stay in registers, and the kernel may use the whole register file of its scheduler (launch bound of one block).
+template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock = false, int kW = 0>
+__global__ void __launch_bounds__(kW ? 32 * kW : tma_threads<kBlock>(), kW == 1 ? 1 : tma_min_blocks<Real, kSummary, kBlock>()) kf_seq_tma_kernel(const __grid_constant__ Params<typename Lanes<Real>::scalar> prm,
                                                                  const __grid_constant__ TmaMaps maps) {
     using Scalar = typename Lanes<Real>::scalar;
     using AccT = typename Acc<Real>::type;
     constexpr int L = Lanes<Real>::n;                     // trajectories per thread
     static_assert(!(kBlock && kMpc), "the element-wise exponential of predict_mpc couples every state");
-    constexpr bool kAccSmem = tma_acc_in_smem<Real, kSummary, kBlock>();  // double / F2 with the full P: the 25 running sums do not fit next to P in registers
+    constexpr bool kAccSmem = kW == 1 ? false : tma_acc_in_smem<Real, kSummary, kBlock>();  // double / F2 with the full P: the 25 running sums do not fit next to P in registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int nt = tma_threads<kBlock>(), TMA_WARPS = tma_warps<kBlock>();
-    using Smem = TmaSmem<Real, nt>;
+    constexpr int TMA_WARPS = kW ? kW : tma_warps<kBlock>(), nt = 32 * TMA_WARPS;
+    // tile sets in flight: the throughput geometry refills a group for step t + 1 as soon as step t's copy has been read (one set; a
+    // second one does not fit next to three resident blocks); the latency variant has the shared memory for two and refills for
+    // step t + 2, so a copy has two whole steps to land (a lone warp waited ~120 cycles per step on the single set)
+    constexpr int kStages = tma_stages<kW>();
+    using Smem = TmaSmem<Real, nt, tma_noise_rows<kOut>(), kStages>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = prm.N, S = prm.S;
     // Block (tile k, group j) filters members W j .. W j + W - 1 of the 32 L streams of tile k (W = warps of the block): warp w owns
@@ -190,25 +204,34 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
     AccT *acc_s = reinterpret_cast<AccT *>(smem_raw + Smem::off_acc(n_lab, kRefRows)) + tid;
 
     if (grp_j * TMA_WARPS * S + tile_k * TW >= N) return;  // the whole block lies beyond the last trajectory (fewer trajectories than streams)
+    const int tile_elems = (int)Smem::warp_rows(n_lab, kRefRows) * 32;  // elements of one tile set
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
+#pragma unroll
+        for (int b = 0; b < 3 * kStages; ++b) mbar_init(&bars[b], 1);  // full[G0], full[G1], full[G2] of every tile set
         consumed[0] = consumed[1] = consumed[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (!warp_active) return;  // fewer members than warps in the last group of a tile
     if (prm.T > 0 && warp == 0) {  // warp 0 of a block always has work
-        issue_g0<kMpc>(maps, 0, s_warp, g0w, refw, &bars[0], lane);
-        issue_g1(maps, 0, s_warp, g1w, &bars[1], lane);
-        if (n_lab) issue_g2(maps, 0, s_warp, n_lab, g2w, &bars[2], lane);
+#pragma unroll
+        for (int sg = 0; sg < kStages; ++sg) {
+            if (sg < prm.T) {
+                issue_g0<kMpc>(maps, sg, s_warp, g0w + sg * tile_elems, refw + sg * tile_elems, &bars[3 * sg], lane);
+                issue_g1(maps, sg, s_warp, g1w + sg * tile_elems, &bars[3 * sg + 1], lane);
+                if (n_lab) issue_g2(maps, sg, s_warp, n_lab, g2w + sg * tile_elems, &bars[3 * sg + 2], lane);
+            }
+        }
     }
     // A warp is done with group g of this step; the LAST warp of the block to get here refills the group for the next step.
     // (The counter is reset before the copy is issued, and nobody can count for the next step before that copy has landed.)
     const auto last_reader = [&](int g) -> int {
         __syncwarp();  // every lane of this warp has read its values
         int last = 0;
+        if constexpr (TMA_WARPS == 1) {  // the block's only warp is always the last reader
+            if (lane == 0) __threadfence_block();
+            return lane == 0 ? 0 : 1;
+        }
         if (lane == 0) {
             __threadfence_block();
             last = atomicAdd(&consumed[g], 1) == n_active - 1;
@@ -225,6 +248,10 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
     for (int c = 0; c < NX; ++c) q[c * nt] = prm.q_kind == OPTI_KF_MAT_DIAG ? Real(prm.Q[c]) : ld_traj(prm.Q, c * N + ic, Real());
 #pragma unroll
     for (int c = 0; c < NZ; ++c) r[c * nt] = prm.r_kind == OPTI_KF_MAT_DIAG ? Real(prm.R[c]) : ld_traj(prm.R, c * N + ic, Real());
+    if constexpr (kOut != 0) {  // K_gain = sum_j P[j][sel j] / r[j] is wanted every step: the ten reciprocals are taken once
+#pragma unroll
+        for (int c = 0; c < NZ; ++c) r[(NZ + c) * nt] = rcp_(r[c * nt]);
+    }
     Real x[NX], P[NP];
 #pragma unroll
     for (int c = 0; c < NX; ++c) x[c] = prm.x0_inc ? ld_traj(prm.x0, c * prm.x0_ld + ic, Real()) : Real(prm.x0[c]);
@@ -290,11 +317,11 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
             }
         }
     };
-    auto trace_of = [](const Real (&Pm)[NP]) {
-        Real tr = Real(0);
+    auto trace_of = [](const Real (&Pm)[NP]) {  // pairwise: a chain of four additions instead of twelve
+        Real h[6];
 #pragma unroll
-        for (int c = 0; c < NX; ++c) tr += Pm[tri(c, c)];
-        return tr;
+        for (int c = 0; c < 6; ++c) h[c] = Pm[tri(2 * c, 2 * c)] + Pm[tri(2 * c + 1, 2 * c + 1)];
+        return ((h[0] + h[1]) + (h[2] + h[3])) + (h[4] + h[5]);
     };
 
     const Real e1_mpc = kMpc ? exp_minus_one(Real(prm.dt)) : Real(0);
@@ -304,17 +331,20 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
     bool any_trunc = may_truncate(Rm);
 
     for (long long t = 0; t < prm.T; ++t) {
-        const uint32_t par = (uint32_t)(t & 1);
-        const bool more = t + 1 < prm.T;
+        const int stg = kStages == 2 ? (int)(t & 1) * tile_elems : 0;  // offset of this step's tile set
+        const uint32_t par = kStages == 2 ? (uint32_t)((t >> 1) & 1) : (uint32_t)(t & 1);
+        const bool more = t + kStages < prm.T;
+        uint64_t *bar = bars + (kStages == 2 ? 3 * (int)(t & 1) : 0);
+        Real *g0 = g0w + stg, *g1 = g1w + stg, *g2 = g2w + stg, *rf = refw + stg;
 
         // ---- G0: feet and forces -> mean model --------------------------------------------------------------
-        mbar_wait(&bars[0], par);
-        propagate_mean_with_R<32>(prm, x, g0w + lane, g0w + 12 * 32 + lane, Rm, any_trunc,
+        mbar_wait(&bar[0], par);
+        propagate_mean_with_R<32>(prm, x, g0 + lane, g0 + 12 * 32 + lane, Rm, any_trunc,
                               (kOut == 2 && active) ? prm.p_world_steps : nullptr, (t * 12) * N + i, N);
         Real E[kMpc ? 9 : 1];  // D[a][6 + k] = exp(dt Rb^T[a][k]) - 1 of the predict_mpc transition (kalman_filter.py:153-157)
         if constexpr (kMpc) {
             Real Rb[9];
-            rot_zyx(refw[lane], refw[32 + lane], refw[64 + lane], Rb);
+            rot_zyx(rf[lane], rf[32 + lane], rf[64 + lane], Rb);
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -322,7 +352,7 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
         }
         {  // this warp has consumed the step's feet and forces: the last one refills G0 for step t + 1
             const int elect = last_reader(0);
-            if (more) issue_g0<kMpc>(maps, t + 1, s_warp, g0w, refw, &bars[0], elect);
+            if (more) issue_g0<kMpc>(maps, t + kStages, s_warp, g0, rf, &bar[0], elect);
         }
         if constexpr (kOut == 2) {
             if (active && prm.x_model_steps) {
@@ -335,11 +365,11 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
         else cov_predict_sym<kBlock>(P, Rm, prm.dt, q, nt);
 
         // ---- G1: measurements, folded in one at a time ---------------------------------------------------------
-        mbar_wait(&bars[1], par);
+        mbar_wait(&bar[1], par);
         if constexpr (kSummary) {
-            if (n_lab) mbar_wait(&bars[2], par);  // G2 (labels, fetched a step ahead like G0 / G1): used inside the last fold
+            if (n_lab) mbar_wait(&bar[2], par);  // G2 (labels, fetched a step ahead like G0 / G1): used inside the last fold
         }
-        const Real *z = g1w + lane;
+        const Real *z = g1 + lane;
         if constexpr (kOut == 2) {
             if (active && prm.z_steps) {
 #pragma unroll
@@ -365,7 +395,7 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
         const Real z9 = z[9 * 32], r9 = r[9 * nt];
         {  // this warp has read its last measurement of the step: the last one refills G1 for step t + 1
             const int elect = last_reader(1);
-            if (more) issue_g1(maps, t + 1, s_warp, g1w, &bars[1], elect);
+            if (more) issue_g1(maps, t + kStages, s_warp, g1, &bar[1], elect);
         }
         fold_pipelined<9, kBlock>(P, x, z9, r9, r9, inv, inv_n, nis, status, [&] {
             // the posterior state is final here: start the next step's sin/cos underneath the last rank-1 update
@@ -375,8 +405,8 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
             // absent one reads a valid dummy tile and is masked at the end), so that its shared-memory round trips are
             // scheduled underneath the 78 independent FMAs of the rank-1 update instead of stalling the tail of the step
             if constexpr (kSummary) {
-                accumulate(0, lab_truth);
-                accumulate(12, lab_nominal);
+                accumulate(0, lab_truth + stg);
+                accumulate(12, lab_nominal + stg);
             }
         });
 
@@ -384,7 +414,7 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
 
         if constexpr (kOut != 0) {
             ptrace = trace_of(P);
-            if (prm.k_gain_steps != nullptr) kgain = gain_trace<kBlock>(P, r, nt);
+            if (prm.k_gain_steps != nullptr) kgain = gain_trace_rinv<kBlock>(P, r + NZ * nt, nt);
             if (active) {
                 if (prm.x_steps) {
 #pragma unroll
@@ -409,7 +439,7 @@ __global__ void __launch_bounds__(tma_threads<kBlock>(), tma_min_blocks<Real, kS
             acc_add(24, to_acc(nis));
             if (n_lab) {
                 const int elect = last_reader(2);  // this warp has consumed the step's labels: the last one refills G2 for step t + 1
-                if (more) issue_g2(maps, t + 1, s_warp, n_lab, g2w, &bars[2], elect);
+                if (more) issue_g2(maps, t + kStages, s_warp, n_lab, g2, &bar[2], elect);
             }
         }
     }

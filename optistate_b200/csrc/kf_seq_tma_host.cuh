@@ -41,7 +41,7 @@ bool make_map(CUtensorMap *m, const Real *base, long long T, int C, long long S,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock>
+template <typename Real, bool kSummary, int kOut, bool kMpc, bool kBlock, int kW = 0>
 int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
     constexpr int L = Lanes<Real>::n;
     const int n_lab = kSummary ? (p.truth ? 1 : 0) + (p.nominal ? 1 : 0) : 0;
@@ -54,9 +54,9 @@ int launch_seq_tma_k(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t
     if (ok && n_lab >= 1) ok = make_map(&maps.lab0, p.truth ? p.truth : p.nominal, p.T, 12, p.S, bw, 12);
     if (ok && n_lab >= 2) ok = make_map(&maps.lab1, p.nominal, p.T, 12, p.S, bw, 12);
     if (!ok) return 1;
-    constexpr int kThreads = tma_threads<kBlock>(), kWarps = tma_warps<kBlock>();
-    const size_t smem = TmaSmem<Real, kThreads>::total(n_lab, kMpc ? TMA_CH_REF : 0, tma_acc_in_smem<Real, kSummary, kBlock>());
-    auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc, kBlock>;
+    constexpr int kWarps = kW ? kW : tma_warps<kBlock>(), kThreads = 32 * kWarps;
+    const size_t smem = TmaSmem<Real, kThreads, tma_noise_rows<kOut>(), tma_stages<kW>()>::total(n_lab, kMpc ? TMA_CH_REF : 0, kW == 1 ? false : tma_acc_in_smem<Real, kSummary, kBlock>());
+    auto kern = kf_seq_tma_kernel<Real, kSummary, kOut, kMpc, kBlock, kW>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return OPTI_KF_E_CUDA;
     // one block per (stream tile, group of kWarps members): see the index mapping at the top of the kernel
     const long long tiles = p.S / (32 * L), n_pass = (p.N + p.S - 1) / p.S;
@@ -91,6 +91,17 @@ int launch_seq_tma(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t s
             default: return launch_seq_tma_k<Real, kSummary, 2, true, false>(p, stream);
         }
     }
+}
+
+// Latency variant (one warp per block, see the kernel): decoupled-group form, predict() covariance model; instantiated in
+// kf_seq_tma_lone_*.cu for double and float.
+template <typename Real, bool kSummary>
+int launch_seq_tma_lone(const Params<typename Lanes<Real>::scalar> &p, cudaStream_t stream) {
+    const bool rare = p.x_model_steps || p.p_world_steps || p.z_steps || p.P_ckpt;
+    const bool estimates = p.x_steps || p.p_trace_steps || p.k_gain_steps || p.nis_steps;
+    if (rare) return launch_seq_tma_k<Real, kSummary, 2, false, true, 1>(p, stream);
+    if (estimates) return launch_seq_tma_k<Real, kSummary, 1, false, true, 1>(p, stream);
+    return launch_seq_tma_k<Real, kSummary, 0, false, true, 1>(p, stream);
 }
 
 }  // namespace okf

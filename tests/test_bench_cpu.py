@@ -46,7 +46,7 @@ def test_current_profiles_describe_the_kernels_that_are_built():
         prof = bench.kernel_profile(dtype, structure, tags=("r2",))
         assert prof is not None, f
         real = {"double": "d", "float": "f", "okf::F2": "NS_2F2E"}[prof["kernel"].split("<")[1].split(",")[0].strip()]
-        mangled = f"kf_seq_tma_kernelI{real}Lb1ELi0ELb0ELb{1 if structure == 'auto' else 0}E"
+        mangled = f"kf_seq_tma_kernelI{real}Lb1ELi0ELb0ELb{1 if structure == 'auto' else 0}ELi0EE"  # ..., kW = 0: the throughput geometry
         hist = sass_loop.loop_histogram(_build.KF_LIB, mangled)
         assert len(hist) == 1, (mangled, list(hist))
         h, _ = next(iter(hist.values()))

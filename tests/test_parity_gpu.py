@@ -264,7 +264,14 @@ def test_full_size_config2_properties():
     assert np.abs(P[:, 0, 0] - 6.1804473556e-03).max() < 1e-9  # SURVEY 8(c) known answer diag(P)[0]
     assert abs(golden_ratio_p - 6.18034e-3) < 1e-8
     assert np.abs(P[:, 3, 3] / (0.01 * T) - 1).max() < 2e-3  # unobserved x variance ~ q * T
-    sample = [0, 511, 1023]
+    # every one of the 1,024 trajectories against the oracle at the end of the 10,000 steps (all host cores: ~1e7 oracle steps) ...
+    full = c_oracle.run(st, want=("x_final", "P_final"))
+    xf = res.x_final.cpu().numpy()
+    assert (np.abs(xf - full["x_final"]).max(axis=1) / np.abs(full["x_final"]).max(axis=1)).max() < 1e-9
+    Pf, Pref = res.P_final.cpu().numpy(), full["P_final"]
+    assert (np.abs(Pf - Pref).max(axis=0) / np.abs(Pref).max(axis=0)).max() < 1e-9  # per trajectory, relative to its largest entry
+    # ... and a sample of them at every step
+    sample = [0, 1, 255, 511, 512, 777, 1022, 1023]
     ref = c_oracle.run({k: np.ascontiguousarray(v[:, :, sample]) for k, v in st.items()}, want=("x_steps", "P_final"))
     x = res.x_steps[:, :, sample].cpu().numpy()
     scale = np.abs(ref["x_steps"]).max(axis=(0, 2))

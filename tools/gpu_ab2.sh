@@ -1,0 +1,4 @@
+export CASE_T=1000
+echo "== base"; LD_LIBRARY_PATH=variants/base python tools/cfg2_latency.py 2>&1 | grep sequential; LD_LIBRARY_PATH=variants/base python tools/rate.py f64:summary f32:summary
+echo "== tree"; python tools/cfg2_latency.py 2>&1 | grep sequential; python tools/rate.py f64:summary f32:summary
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_peer_gpu.py -m gpu -x -q 2>&1 | tail -3
