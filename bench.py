@@ -137,9 +137,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--e2e-upload", default="replicated", choices=["shared", "shared-lowprio", "replicated"],
+    ap.add_argument("--e2e-upload", default="auto", choices=["auto", "shared", "shared-lowprio", "replicated"],
                     help="N > 1, e2e: every rank uploads all base streams (replicated), or 1/N of them + an NVLink all-gather on a "
-                         "high-priority NCCL stream (shared) / on NCCL's default stream (shared-lowprio)")
+                         "high-priority NCCL stream (shared) / on NCCL's default stream (shared-lowprio); auto = shared from 4 GPUs up, "
+                         "where the host interface bounds the replicated upload (profiles/r2_e2e_upload_modes.txt)")
+    ap.add_argument("--e2e-trace", action="store_true", help="add the per-batch event timeline of the host pipeline (rank 0) to the e2e object")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: all-gather of the summaries fused into the filter kernel (NVLink peer stores) or NCCL after it")
     return ap.parse_args()
@@ -555,12 +557,14 @@ def run_native(a):
         # N > 1: the ranks filter different members of the SAME base streams; with --e2e-upload shared each uploads 1/N of the stream
         # arrays and the slices are exchanged over NVLink (pipeline.py); per-member noise and summaries are per rank
         exchange_group = None
+        if a.e2e_upload == "auto":
+            a.e2e_upload = "shared" if world >= 4 else "replicated"
         if world > 1 and a.e2e_upload != "replicated":
             from optistate_b200.distributed import stream_exchange_group
 
             exchange_group = stream_exchange_group() if a.e2e_upload == "shared" else dist.group.WORLD
         pipe = KfHostPipeline(n_local, T, S, dtype=dtype, labels=("truth", "nominal"), stream_offset=first, structure=a.structure,
-                              shared_streams_group=exchange_group)
+                              shared_streams_group=exchange_group, trace=a.e2e_trace)
         for _ in range(max(2, a.warmup - 1)):
             step_e2e()
         finish_e2e()
@@ -587,6 +591,8 @@ def run_native(a):
                "api": "optistate_b200.pipeline.KfHostPipeline (kf_batch on pinned host buffers, double-buffered)" +
                       ("; base streams uploaded once per job (1/N per rank) and all-gathered over NVLink" if pipe.world > 1 else "")}
 
+    if e2e is not None and a.e2e_trace:
+        e2e["timeline_ms"] = pipe.timeline()
     if peer is not None:
         peer.close()
     if rank != 0:

@@ -10,8 +10,9 @@ of batch k, so sustained end-to-end throughput is max(compute, copies) instead o
 
 Several GPUs filtering different members of the SAME base streams (the Monte-Carlo sweep: one process per GPU, contiguous shards
 of the members): with `shared_streams_group` every rank uploads only its 1/world slice of the stream arrays over PCIe and the
-ranks exchange the slices over NVLink (one in-place NCCL all-gather per batch on the upload stream), so every byte of the
-streams crosses the host interface once per batch instead of once per GPU.  Per-member noise and summaries stay per rank.
+ranks exchange the slices over NVLink (one in-place NCCL all-gather per batch, queued LAST on the upload stream), so every byte of
+the streams crosses the host interface once per batch instead of once per GPU.  Per-member noise and summaries stay per rank.
+Measured on one 8-GPU B200 box: 59.9 against 65.1 ms per batch at 4 GPUs, 67.1 against 79.9 ms at 8 (profiles/r2_e2e_upload_modes.txt).
 """
 from __future__ import annotations
 
@@ -28,7 +29,7 @@ _STREAM_CH = {"imu": 6, "p": 12, "dp": 12, "contact": 4, "f": 12, "truth": 12, "
 class KfHostPipeline:
     def __init__(self, n_traj: int, n_steps: int, n_streams: int, *, dtype: torch.dtype = torch.float64,
                  labels: Sequence[str] = ("truth", "nominal"), stream_offset: int = 0, n_slots: int = 2, device=None,
-                 structure: str = "auto", shared_streams_group=None):
+                 structure: str = "auto", shared_streams_group=None, trace: bool = False):
         nv.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n_traj, self.n_steps, self.n_streams, self.dtype = n_traj, n_steps, n_streams, dtype
@@ -65,6 +66,9 @@ class KfHostPipeline:
                                "ev_out": torch.cuda.Event(), "busy": False})
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
         self._next = 0
+        # trace: timed events per submitted batch (upload start / uploads done / inputs complete / kernel start / kernel done / result on
+        # the host), read back with timeline() - a development aid for the multi-GPU pipeline, off by default
+        self._trace = [] if trace else None
 
     def submit(self, host: Dict[str, torch.Tensor]) -> int:
         """Queues one batch (pinned host tensors) and returns its ticket; blocks only if all slots are still in flight."""
@@ -74,9 +78,15 @@ class KfHostPipeline:
         if slot["busy"]:
             slot["ev_out"].synchronize()  # the previous result of this slot must have left the device
         dev = slot["dev"]
+        tr = None
+        if self._trace is not None:
+            tr = {k: torch.cuda.Event(enable_timing=True) for k in ("in0", "in1", "in2", "k0", "k1", "o1")}
+            self._trace.append(tr)
         with torch.cuda.stream(self.s_in):
             if slot["busy"]:
                 self.s_in.wait_event(slot["ev_k"])  # do not overwrite inputs a kernel may still be reading
+            if tr:
+                tr["in0"].record(self.s_in)
             copied = 0
             if self.world == 1:
                 for k, d in dev.items():
@@ -93,23 +103,37 @@ class KfHostPipeline:
                     if lo < hi:
                         flat[lo:hi].copy_(host[k].reshape(-1)[lo - a:hi - a], non_blocking=True)
                         copied += hi - lo
-                dist.all_gather_into_tensor(flat, flat[c0:c1], group=self.group)
                 for k in ("Q", "R"):
                     dev[k].copy_(host[k], non_blocking=True)
                     copied += dev[k].numel()
+                if tr:
+                    tr["in1"].record(self.s_in)
+                # LAST on this stream: the exchange is a kernel with large blocks and only gets onto the SMs when the filter kernel of
+                # the previous batch drains, so nothing that could run underneath that kernel may queue behind it (with the noise upload
+                # after it, that upload - 185 MB per rank at the contended host rate - sat between two filter kernels: +12 - 18 ms per
+                # step at 4 - 8 GPUs, profiles/r2_e2e_upload_modes.txt)
+                dist.all_gather_into_tensor(flat, flat[c0:c1], group=self.group)
             self.h2d_bytes_per_batch = copied * (8 if self.dtype == torch.float64 else 4)
             slot["ev_in"].record(self.s_in)
+            if tr:
+                tr["in2"].record(self.s_in)
         with torch.cuda.stream(self.s_k):
             self.s_k.wait_event(slot["ev_in"])
+            if tr:
+                tr["k0"].record(self.s_k)
             kf_batch(dev["imu"], dev["p"], dev["dp"], dev["contact"], dev["f"], Q=dev["Q"], R=dev["R"], n_traj=self.n_traj,
                      dtype=self.dtype, stream_offset=self.stream_offset, truth=dev.get("truth"), nominal=dev.get("nominal"),
                      outputs=("summary",), out=slot["out"], q_kind=nv.MAT_DIAG_PER, r_kind=nv.MAT_DIAG_PER, device=self.device,
                      structure=self.structure)
             slot["ev_k"].record(self.s_k)
+            if tr:
+                tr["k1"].record(self.s_k)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot["ev_k"])
             slot["host"].copy_(slot["out"]["summary"], non_blocking=True)
             slot["ev_out"].record(self.s_out)
+            if tr:
+                tr["o1"].record(self.s_out)
         slot["busy"] = True
         return i
 
@@ -123,3 +147,22 @@ class KfHostPipeline:
         for slot in self.slots:
             if slot["busy"]:
                 slot["ev_out"].synchronize()
+
+    def timeline(self):
+        """With trace=True: per submitted batch, milliseconds from the first batch's upload start to its events (drain() first)."""
+        if not self._trace:
+            return []
+        self.drain()
+        torch.cuda.synchronize(self.device)
+        base = self._trace[0]["in0"]
+        out = []
+        for tr in self._trace:
+            row = {}
+            for k, ev in tr.items():
+                try:
+                    row[k] = round(base.elapsed_time(ev), 2)
+                except Exception:  # an event that was never recorded (in1 outside the shared upload mode)
+                    row[k] = None
+            out.append(row)
+        return out
+
