@@ -28,7 +28,14 @@
 
 namespace okf {
 
-constexpr int MPCG_WARPS = 5;       // problems per block of the one-warp kernel: 3 blocks = 15 warps per SM fit the shared memory (14.7 KB per problem)
+#ifndef OKF_MPCG_WARPS
+#define OKF_MPCG_WARPS 5
+#endif
+constexpr int MPCG_WARPS = OKF_MPCG_WARPS;  // problems per block of the one-warp kernel: 3 blocks = 15 warps per SM fit the shared memory (14.7 KB per problem)
+// (Measured alternatives, same box: one warp per block x 14 blocks - no block-level tail behind a long active-set sequence, but one warp
+// less per SM - 2.57e7 against 2.75e7 trot QPs/s and 2.03e7 against 2.55e7 closed-loop steps/s; two warps x 7 blocks 2.70e7 / 2.23e7.)
+// resident blocks per SM the kernel is compiled for: what 227 KB of shared memory hold (each block also costs 1 KB of system shared memory)
+constexpr int MPCG_MIN_BLOCKS = MPCG_WARPS == 5 ? 3 : (MPCG_WARPS == 1 ? 14 : (MPCG_WARPS == 2 ? 7 : 3));
 constexpr int MPCG_MAX_IT = 400;    // constraints added + dropped
 // capacity of the working set for 1..4 legs out of swing (linear independence bounds it by the order n = 15 legs; the test
 // batches peak at 21 for two legs and 43 for four).  A problem that needs more is handed to the interior point.
@@ -495,7 +502,7 @@ __device__ __forceinline__ void mpc_solve_gi(const MpcParams &prm, long long pro
 }
 
 // One warp per problem (at most two legs out of swing); prm.status is required (the second launch reads the flags).
-__global__ void __launch_bounds__(32 * MPCG_WARPS, 3) kf_mpc_gi_kernel(const __grid_constant__ MpcParams prm) {
+__global__ void __launch_bounds__(32 * MPCG_WARPS, MPCG_MIN_BLOCKS) kf_mpc_gi_kernel(const __grid_constant__ MpcParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long prob = (long long)blockIdx.x * MPCG_WARPS + warp;
