@@ -8,15 +8,18 @@ F_d, B_d), same methods and the same side effects:
   * `predict` / `update` rebind `self.x` / `self.P` to new arrays (kalman_filter.py:133-135,169-172), so the
     STARTING_STATE / Q aliases are only mutated by callers that assign through `KF.x[:] = ...`.
 Every numerical method runs on the GPU through the C ABI (one trajectory, one step, the JOINT kernel which keeps
-the reference's operand order on a full non-symmetrised P); there is no CPU implementation behind it.
-For many trajectories or many steps use `optistate_b200.kf_batch`, which runs the same arithmetic in one launch.
+the reference's operand order on a full non-symmetrised P); there is no CPU implementation behind it.  A method is one call of
+the binding on a pinned block the kernels write their results into, and `predict` already launches the update that follows
+it (see `_buffers`): 11 - 12 k steps/s stepped the way the reference driver steps it, against 4.7 - 4.9 k for the reference
+class on one core of the same box.  For many trajectories or many steps use `optistate_b200.kf_batch`, which runs the
+same arithmetic in one launch.
 
 Errors follow the reference: `numpy.linalg.LinAlgError` when S is not invertible (kalman_filter.py:168) and
 `ValueError` when no foot is in stance (kalman_filter.py:97-103).
 
 The forces inside `predict_mpc` come from the reference's convex MPC (CasADi + qpOASES, force_controller.py:15-225).  Here
-they are solved for on the device by optistate_b200.mpc.mpc_forces (same QP, interior point + active-set polish; parity
-with qpOASES unpinned, see there), unless forces are passed explicitly (`f=`) or an injectable `force_provider` is set.
+they are solved for on the device by optistate_b200.mpc.mpc_forces (same QP; dual active-set kernels with an interior
+point behind them; parity with qpOASES unpinned, see there), unless forces are passed explicitly (`f=`) or an injectable `force_provider` is set.
 """
 from __future__ import annotations
 
