@@ -26,6 +26,26 @@ from .batch import kf_batch
 _STREAM_CH = {"imu": 6, "p": 12, "dp": 12, "contact": 4, "f": 12, "truth": 12, "nominal": 12}
 
 
+def stream_share_plan(sizes: Dict[str, int], world: int, rank: int):
+    """Shared upload: the stream arrays of a slot live back to back in one flat allocation, padded to a multiple of `world`; rank r
+    owns elements [r, r + 1) * flat_len / world of it.  Returns (flat_len, {name: (begin, end)} of every array in the flat
+    allocation, [(name, begin_in_array, begin_in_flat, count)] = the pieces rank `rank` uploads).  Pure arithmetic (CPU-testable):
+    over all ranks the pieces tile every array exactly once."""
+    ranges, off = {}, 0
+    for k, n in sizes.items():
+        ranges[k] = (off, off + int(n))
+        off += int(n)
+    flat_len = (off + world - 1) // world * world
+    share = flat_len // world
+    c0, c1 = rank * share, (rank + 1) * share
+    pieces = []
+    for k, (a, b) in ranges.items():
+        lo, hi = max(a, c0), min(b, c1)
+        if lo < hi:
+            pieces.append((k, lo - a, lo, hi - lo))
+    return flat_len, ranges, pieces
+
+
 class KfHostPipeline:
     def __init__(self, n_traj: int, n_steps: int, n_streams: int, *, dtype: torch.dtype = torch.float64,
                  labels: Sequence[str] = ("truth", "nominal"), stream_offset: int = 0, n_slots: int = 2, device=None,
@@ -44,13 +64,7 @@ class KfHostPipeline:
             self.world, self.rank = dist.get_world_size(shared_streams_group), dist.get_rank(shared_streams_group)
         # the stream arrays of a slot live back to back in one allocation (padded to a multiple of the world size), so that a rank's
         # share is one contiguous range of it
-        sizes = [n_steps * _STREAM_CH[k] * n_streams for k in names]
-        total = sum(sizes)
-        self._flat_len = (total + self.world - 1) // self.world * self.world
-        self._ranges, off = {}, 0
-        for k, n in zip(names, sizes):
-            self._ranges[k] = (off, off + n)
-            off += n
+        self._flat_len, self._ranges, self._pieces = stream_share_plan({k: n_steps * _STREAM_CH[k] * n_streams for k in names}, self.world, self.rank)
         self.h2d_bytes_per_batch = 0  # what this rank copies from the host per submit (set below)
         self.slots = []
         for _ in range(n_slots):
@@ -98,11 +112,9 @@ class KfHostPipeline:
 
                 flat, share = slot["flat"], self._flat_len // self.world
                 c0, c1 = self.rank * share, (self.rank + 1) * share
-                for k, (a, b) in self._ranges.items():
-                    lo, hi = max(a, c0), min(b, c1)
-                    if lo < hi:
-                        flat[lo:hi].copy_(host[k].reshape(-1)[lo - a:hi - a], non_blocking=True)
-                        copied += hi - lo
+                for k, src0, dst0, cnt in self._pieces:
+                    flat[dst0:dst0 + cnt].copy_(host[k].reshape(-1)[src0:src0 + cnt], non_blocking=True)
+                    copied += cnt
                 for k in ("Q", "R"):
                     dev[k].copy_(host[k], non_blocking=True)
                     copied += dev[k].numel()

@@ -65,6 +65,58 @@ def test_summary_all_gather_world_size_2_gloo(tmp_path):
         assert p.returncode == 0 and "ok" in out, err[-2000:]
 
 
+_SHARE_WORKER = """
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from optistate_b200.distributed import stream_exchange_group
+from optistate_b200.pipeline import stream_share_plan
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+grp = stream_exchange_group()  # gloo: a plain group (the high-priority option is NCCL's)
+rank = dist.get_rank()
+sizes = {"imu": 7 * 6 * 3, "p": 7 * 12 * 3, "contact": 7 * 4 * 3 + 1}  # odd total: the flat allocation is padded
+rng = np.random.default_rng(5)
+host = {k: torch.from_numpy(rng.standard_normal(n)) for k, n in sizes.items()}  # the same on both ranks
+flat_len, ranges, pieces = stream_share_plan(sizes, 2, rank)
+flat = torch.full((flat_len,), float("nan"), dtype=torch.float64)
+for k, src0, dst0, cnt in pieces:  # this rank's share only
+    flat[dst0:dst0 + cnt] = host[k][src0:src0 + cnt]
+share = flat_len // 2
+mine = flat[rank * share:(rank + 1) * share].clone()
+parts = [torch.empty(share, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(parts, mine, group=grp)  # (gloo has no all_gather_into_tensor: same exchange, list form)
+full = torch.cat(parts)
+for k, (a, b) in ranges.items():
+    assert torch.equal(full[a:b], host[k]), k
+dist.barrier(); dist.destroy_process_group(); print("ok")
+"""
+
+
+def test_shared_stream_upload_plan_tiles_every_array_once_and_exchanges_over_gloo(tmp_path):
+    """KfHostPipeline's shared upload: every rank uploads its 1/world share of the flat stream allocation, one all-gather completes
+    it on every rank.  The plan is pure arithmetic; the exchange is checked with world_size 2 over gloo."""
+    from optistate_b200.pipeline import stream_share_plan
+
+    sizes = {"a": 10, "b": 3, "c": 24, "d": 1}
+    for world in (1, 2, 3, 4, 8):
+        seen = {k: np.zeros(n, dtype=np.int64) for k, n in sizes.items()}
+        for rank in range(world):
+            flat_len, ranges, pieces = stream_share_plan(sizes, world, rank)
+            assert flat_len % world == 0 and flat_len >= sum(sizes.values()) and ranges["a"] == (0, 10) and ranges["d"] == (37, 38)
+            share = flat_len // world
+            for k, src0, dst0, cnt in pieces:
+                assert dst0 == ranges[k][0] + src0 and rank * share <= dst0 and dst0 + cnt <= (rank + 1) * share
+                seen[k][src0:src0 + cnt] += 1
+        assert all((v == 1).all() for v in seen.values()), world
+    script = tmp_path / "w.py"
+    script.write_text(_SHARE_WORKER)
+    port = str(27500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, err[-2000:]
+
+
 def test_bench_noise_is_a_function_of_the_member_id():
     sys.path.insert(0, ROOT)
     import bench
