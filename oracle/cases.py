@@ -72,6 +72,19 @@ def build(name: str):
         s = make_stream(26, 200)
         s["imu"][:, 0:3] += np.array([0.9, -1.2, 2.8])
         return s, kw, 1
+    if name == "edge_diag_p0_seed31":  # a diagonal P0 that is NOT Q (the decoupled-group kernels take any diagonal P0), Q_R.pkl noise
+        rng = np.random.default_rng(31)
+        kw["Q"], kw["R"] = q_r_pkl()
+        kw["P0"] = np.diag(rng.uniform(1e-3, 0.5, 12))
+        kw["x0"] = START + 0.02 * rng.standard_normal(12)
+        return make_stream(31, 300), kw, 1
+    if name == "edge_block_p0_seed32":  # a dense P0 with entries inside the groups {th, w}, {x, vx}, {y, vy}, {z, vz} only
+        rng = np.random.default_rng(32)
+        grp = np.array([0, 0, 0, 1, 2, 3, 0, 0, 0, 1, 2, 3])
+        A = _spd(rng, 12, 0.03)
+        kw["P0"] = np.where(grp[:, None] == grp[None, :], A, 0.0)
+        kw["x0"] = START + 0.02 * rng.standard_normal(12)
+        return make_stream(32, 300), kw, 1
     if name == "next_mpc_cov_seed5":  # predict_mpc covariance model with supplied f
         s = make_stream(5, 400)
         s["body_ref"] = s["truth"].copy()
@@ -84,7 +97,7 @@ def build(name: str):
 ALL_CASES = [
     "cfg1_default_seed0", "default_seed11_10k", "stress_qrpkl_seed3_10k", "edge_zero_attitude_spin",
     "edge_yaw_quarter_turn", "edge_dense_noise", "edge_nonsymmetric_p0", "edge_contact_patterns",
-    "edge_large_angles", "next_mpc_cov_seed5",
+    "edge_large_angles", "next_mpc_cov_seed5", "edge_diag_p0_seed31", "edge_block_p0_seed32",
 ]
 
 

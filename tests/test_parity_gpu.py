@@ -12,7 +12,7 @@ from tests import parity
 pytestmark = pytest.mark.gpu
 
 ALL_OUT = ("x_steps", "x_model_steps", "p_world_steps", "z_steps", "p_trace_steps", "k_gain_steps", "P_ckpt", "final")
-DIAG_CASES = ["cfg1_default_seed0", "default_seed11_10k", "stress_qrpkl_seed3_10k", "edge_zero_attitude_spin",
+DIAG_CASES = ["edge_diag_p0_seed31", "edge_block_p0_seed32", "cfg1_default_seed0", "default_seed11_10k", "stress_qrpkl_seed3_10k", "edge_zero_attitude_spin",
               "edge_yaw_quarter_turn", "edge_contact_patterns", "edge_large_angles"]
 JOINT_ONLY = ["edge_dense_noise", "edge_nonsymmetric_p0"]
 
@@ -58,7 +58,8 @@ def compare_golden(name, res, tol_x, tol_p, tol_tr):
 @pytest.mark.parametrize("algo", ["sequential", "sequential-full", "joint"])
 def test_fp64_matches_reference_golden(name, algo):
     """north_star: FP64 within 1e-9 relative on states and covariances.  "sequential" runs the decoupled-group kernels
-    (these cases start from a diagonal P0), "sequential-full" the same recursion on all 78 packed entries."""
+    (these cases start from a diagonal P0 - Q itself, or another diagonal - or from a dense P0 whose entries lie inside the
+    groups, which the host detects), "sequential-full" the same recursion on all 78 packed entries."""
     kw = dict(structure="full") if algo == "sequential-full" else {}
     algo = algo.split("-")[0]
     res = run_case(name, algo, **kw)

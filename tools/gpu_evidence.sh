@@ -1,4 +1,4 @@
-# Final round-2 evidence on one B200 (after the latency variant / drop-in / warm-start changes).  Outputs: gpurun_out/r2z/
+# Round-2 evidence on one B200: tests, bench lines, ncu captures of the timed kernels and of the latency variant, launch list, smoke, rates.  Outputs: gpurun_out/r2z/
 O=gpurun_out/r2z
 mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.txt
