@@ -562,7 +562,11 @@ def run_native(a):
         if world > 1 and a.e2e_upload != "replicated":
             from optistate_b200.distributed import stream_exchange_group
 
-            exchange_group = stream_exchange_group() if a.e2e_upload == "shared" else dist.group.WORLD
+            try:
+                exchange_group = stream_exchange_group() if a.e2e_upload == "shared" else dist.group.WORLD
+            except Exception as e:  # a build of torch without the NCCL options: every rank fails alike and uploads everything itself
+                print(f"bench: no high-priority exchange group ({e}); replicated upload", file=sys.stderr)
+                exchange_group, a.e2e_upload = None, "replicated"
         pipe = KfHostPipeline(n_local, T, S, dtype=dtype, labels=("truth", "nominal"), stream_offset=first, structure=a.structure,
                               shared_streams_group=exchange_group, trace=a.e2e_trace)
         for _ in range(max(2, a.warmup - 1)):
