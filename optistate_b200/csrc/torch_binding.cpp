@@ -469,42 +469,6 @@ std::pair<double, double> fma_peak(int64_t dtype, int64_t fma_per_thread) {
     return {flops, secs};
 }
 
-// One trajectory, one call of the drop-in class (optistate_b200/kalman_filter.py): the inputs sit packed in a pinned host
-// buffer, the layout lists (name, element count) in order.  Upload, launch (kf_batch, or kf_measure when cfg is empty),
-// download of the packed outputs and of the status word, ONE stream synchronisation - all below the Python dispatcher,
-// which is what a single-step call is made of (the launch itself is ~10 us).  Returns the C ABI's return code.
-int64_t kf_host_call(const std::map<std::string, int64_t> &cfg, const std::map<std::string, double> &consts,
-                     const std::vector<std::pair<std::string, int64_t>> &in_layout, const std::vector<std::pair<std::string, int64_t>> &out_layout,
-                     const at::Tensor &h_in, at::Tensor d_in, at::Tensor d_out, at::Tensor h_out, at::Tensor d_status, at::Tensor h_status) {
-    TORCH_CHECK(d_in.is_cuda() && d_out.is_cuda() && d_status.is_cuda(), "optistate_b200: device buffers must be CUDA tensors (there is no CPU path)");
-    TORCH_CHECK(h_in.is_pinned() && h_out.is_pinned() && h_status.is_pinned(), "optistate_b200: host buffers must be pinned");
-    const c10::cuda::CUDAGuard guard(d_in.device());
-    cudaStream_t stream = at::cuda::getCurrentCUDAStream().stream();
-    TensorMap tensors;
-    int64_t n_in = 0, n_out = 0;
-    for (const auto &kv : in_layout) {
-        tensors[kv.first] = d_in.narrow(0, n_in, kv.second);
-        n_in += kv.second;
-    }
-    for (const auto &kv : out_layout) {
-        tensors[kv.first] = d_out.narrow(0, n_out, kv.second);
-        n_out += kv.second;
-    }
-    TORCH_CHECK(n_in <= h_in.numel() && n_in <= d_in.numel() && n_out <= d_out.numel() && n_out <= h_out.numel(), "optistate_b200: layout exceeds the buffers");
-    tensors["status"] = d_status;
-    const size_t esz = d_in.element_size();
-    TORCH_CHECK(cudaMemcpyAsync(d_in.data_ptr(), h_in.data_ptr(), n_in * esz, cudaMemcpyHostToDevice, stream) == cudaSuccess, "upload failed");
-    TORCH_CHECK(cudaMemsetAsync(d_status.data_ptr(), 0, sizeof(int32_t), stream) == cudaSuccess, "memset failed");
-    const int64_t rc = cfg.empty() ? (int64_t)kf_measure(d_in.scalar_type() == at::kDouble ? OPTI_KF_F64 : OPTI_KF_F32, 1, 1, tensors)
-                                   : kf_batch(cfg, consts, tensors);
-    if (rc != 0) return rc;
-    TORCH_CHECK(cudaMemcpyAsync(h_out.data_ptr(), d_out.data_ptr(), n_out * esz, cudaMemcpyDeviceToHost, stream) == cudaSuccess, "download failed");
-    TORCH_CHECK(cudaMemcpyAsync(h_status.data_ptr(), d_status.data_ptr(), sizeof(int32_t), cudaMemcpyDeviceToHost, stream) == cudaSuccess, "download failed");
-    TORCH_CHECK(cudaStreamSynchronize(stream) == cudaSuccess, "optistate_b200: the launch failed");
-    return 0;
-}
-
-
 // ---- the drop-in class's step (optistate_b200/kalman_filter.py) through ONE call of this binding ------------------------------
 // The class keeps one pinned host block with a FIXED layout (the offsets below, in doubles; kalman_filter.py mirrors them) and a device
 // block of the same size.  `ops` says which of the reference's methods run, in the reference's order: get_odom + the measurement
@@ -610,7 +574,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "PyTorch loader of liboptistate_kf.so (C ABI in include/optistate_kf.h)";
     m.def("kf_batch", &kf_batch);
     m.def("kf_measure", &kf_measure);
-    m.def("kf_host_call", &kf_host_call);
     m.def("kf_class_step", &kf_class_step);
     m.def("kf_resolve_algo", &kf_resolve_algo);
     m.def("fma_peak", &fma_peak);
